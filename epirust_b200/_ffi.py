@@ -1,0 +1,114 @@
+"""ctypes binding of the C ABI in include/epi.h (epirust_b200/libepirust_b200.so).
+
+Fails loudly when the CUDA library is missing: there is no CPU fallback in the product.
+"""
+import ctypes as C
+import os
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG, "libepirust_b200.so")
+
+EPI_DRAWS_PER_AGENT = 16
+EPI_N_KERNEL_KINDS = 8
+KERNEL_KINDS = ("hour", "commit", "hospital_scan", "sleep", "sweep", "pack", "unpack", "misc")
+
+
+class EpiConfig(C.Structure):
+    """`epi_config` of include/epi.h (== common::config::Config for Population::Auto)."""
+
+    _fields_ = [
+        ("number_of_agents", C.c_uint32),
+        ("public_transport_percentage", C.c_double),
+        ("working_percentage", C.c_double),
+        ("regular_transmission_start_day", C.c_uint32),
+        ("high_transmission_start_day", C.c_uint32),
+        ("last_day", C.c_uint32),
+        ("asymptomatic_last_day", C.c_uint32),
+        ("mild_infected_last_day", C.c_uint32),
+        ("regular_transmission_rate", C.c_double),
+        ("high_transmission_rate", C.c_double),
+        ("death_rate", C.c_double),
+        ("percentage_asymptomatic_population", C.c_double),
+        ("percentage_severe_infected_population", C.c_double),
+        ("exposed_duration", C.c_uint32),
+        ("pre_symptomatic_duration", C.c_uint32),
+        ("grid_size", C.c_uint32),
+        ("hospital_beds_percentage", C.c_double),
+        ("hours", C.c_uint32),
+        ("infected_mild_asymptomatic", C.c_uint32),
+        ("infected_mild_symptomatic", C.c_uint32),
+        ("infected_severe", C.c_uint32),
+        ("exposed", C.c_uint32),
+        ("has_lockdown", C.c_int32),
+        ("lockdown_at_number_of_infections", C.c_uint32),
+        ("essential_workers_population", C.c_double),
+        ("has_build_new_hospital", C.c_int32),
+        ("spread_rate_threshold", C.c_uint32),
+        ("n_vaccinations", C.c_int32),
+        ("vaccinate_at_hour", C.c_uint32 * 8),
+        ("vaccinate_percent", C.c_double * 8),
+    ]
+
+
+class EpiCounts(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in ("hour", "susceptible", "exposed", "infected", "hospitalized", "recovered", "deceased")]
+
+
+# every symbol include/epi.h declares (tests/test_abi.py checks the library exports all of them)
+EXPORTS = [
+    "epi_create", "epi_create_region", "epi_destroy", "epi_last_error", "epi_population", "epi_counts_at_start", "epi_set_stream",
+    "epi_sync", "epi_reset", "epi_step", "epi_step_with_draws", "epi_run_hours", "epi_lock_city", "epi_unlock_city", "epi_vaccinate",
+    "epi_expand_hospital", "epi_get_state", "epi_set_state", "epi_geometry", "epi_get_grid", "epi_set_kernel_timing",
+    "epi_get_kernel_times", "epi_launch_count", "epi_device_bytes", "epi_config_from_json", "epi_config_from_json_string",
+    "epi_run_standalone", "epi_version",
+]
+
+_lib = None
+
+
+def load():
+    """Load the CUDA shared library; raise if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -m epirust_b200.build` (nvcc, sm_100a). "
+            "epirust_b200 has no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, u32, u64, i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int
+    L.epi_create.argtypes = [C.POINTER(EpiConfig), u64, i32, C.POINTER(vp)]
+    L.epi_create_region.argtypes = [C.POINTER(EpiConfig), u64, i32, i32, C.POINTER(vp)]
+    L.epi_destroy.argtypes = [vp]
+    L.epi_destroy.restype = None
+    L.epi_last_error.argtypes = [vp]
+    L.epi_last_error.restype = C.c_char_p
+    L.epi_population.argtypes = [vp]
+    L.epi_population.restype = u32
+    L.epi_counts_at_start.argtypes = [vp, C.POINTER(EpiCounts)]
+    L.epi_set_stream.argtypes = [vp, vp]
+    L.epi_sync.argtypes = [vp]
+    L.epi_reset.argtypes = [vp]
+    L.epi_step.argtypes = [vp, u32, C.POINTER(EpiCounts)]
+    L.epi_step_with_draws.argtypes = [vp, u32, vp, C.POINTER(EpiCounts)]
+    L.epi_run_hours.argtypes = [vp, u32, u32, vp]
+    L.epi_lock_city.argtypes = [vp]
+    L.epi_unlock_city.argtypes = [vp]
+    L.epi_vaccinate.argtypes = [vp, C.c_double, u32]
+    L.epi_expand_hospital.argtypes = [vp]
+    L.epi_get_state.argtypes = [vp] + [vp] * 7
+    L.epi_set_state.argtypes = [vp, u32] + [vp] * 7
+    L.epi_geometry.argtypes = [vp, vp]
+    L.epi_get_grid.argtypes = [vp, vp, u64, C.POINTER(u32), C.POINTER(u32)]
+    L.epi_set_kernel_timing.argtypes = [vp, i32]
+    L.epi_get_kernel_times.argtypes = [vp, vp, vp]
+    L.epi_launch_count.argtypes = [vp, i32]
+    L.epi_launch_count.restype = u64
+    L.epi_device_bytes.argtypes = [vp]
+    L.epi_device_bytes.restype = u64
+    L.epi_config_from_json.argtypes = [C.c_char_p, C.POINTER(EpiConfig)]
+    L.epi_config_from_json_string.argtypes = [C.c_char_p, C.POINTER(EpiConfig)]
+    L.epi_run_standalone.argtypes = [C.POINTER(EpiConfig), u64, i32, C.c_char_p, C.c_char_p, vp, u32, C.POINTER(u32), C.POINTER(C.c_double)]
+    L.epi_version.restype = C.c_char_p
+    _lib = L
+    return L

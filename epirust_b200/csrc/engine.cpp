@@ -1,0 +1,560 @@
+// C ABI of include/epi.h: engine lifecycle, the per-hour step, interventions sweeps, state import/export, measurement.
+#include "engine.h"
+
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+#include <stdexcept>
+
+#include "kernels.h"
+#include "philox.cuh"
+
+using namespace epi;
+
+namespace epi {
+static std::mutex g_err_mutex;
+static std::string g_err;
+void set_global_error(const std::string& msg) {
+    std::lock_guard<std::mutex> lk(g_err_mutex);
+    g_err = msg;
+}
+int engine_fail(const epi_engine* e, int code, const std::string& msg) {
+    if (e) e->err = msg;
+    else set_global_error(msg);
+    return code;
+}
+}  // namespace epi
+
+#define CU(call)                                                                                                   \
+    do {                                                                                                           \
+        cudaError_t _err = (call);                                                                                 \
+        if (_err != cudaSuccess)                                                                                   \
+            return engine_fail(e, EPI_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_err));              \
+    } while (0)
+
+enum KernelKind { KK_HOUR = 0, KK_COMMIT = 1, KK_SCAN = 2, KK_SLEEP = 3, KK_SWEEP = 4, KK_PACK = 5, KK_UNPACK = 6, KK_MISC = 7 };
+
+namespace {
+
+template <class T>
+cudaError_t dev_alloc(epi_engine* e, T** p, size_t count) {
+    cudaError_t r = cudaMalloc((void**)p, count * sizeof(T));
+    if (r == cudaSuccess) e->device_bytes += count * sizeof(T);
+    return r;
+}
+
+// bracket one launch with events when per-kernel timing is on
+struct Timed {
+    epi_engine* e;
+    int kind;
+    cudaEvent_t a = nullptr, b = nullptr;
+    Timed(epi_engine* e_, int kind_) : e(e_), kind(kind_) {
+        e->launches++;
+        e->kernel_launches[kind]++;
+        if (e->timing) {
+            cudaEventCreate(&a);
+            cudaEventCreate(&b);
+            cudaEventRecord(a, e->stream);
+        }
+    }
+    ~Timed() {
+        if (e->timing) {
+            cudaEventRecord(b, e->stream);
+            e->pending_events.push_back({kind, {a, b}});
+        }
+    }
+};
+
+void drain_events(epi_engine* e) {
+    for (auto& pe : e->pending_events) {
+        float ms = 0.f;
+        cudaEventSynchronize(pe.second.second);
+        cudaEventElapsedTime(&ms, pe.second.first, pe.second.second);
+        e->kernel_ms[pe.first] += ms;
+        cudaEventDestroy(pe.second.first);
+        cudaEventDestroy(pe.second.second);
+    }
+    e->pending_events.clear();
+}
+
+size_t n_cells(const epi_engine* e) { return (size_t)e->geo.pitch * e->geo.rows; }
+
+int rebuild_grid(epi_engine* e) {
+    CU(cudaMemsetAsync(e->D.grid, 0, n_cells(e), e->stream));
+    CU(cudaMemsetAsync(e->d_misc, 0, 2 * sizeof(uint32_t), e->stream));
+    {
+        Timed t(e, KK_MISC);
+        launch_build_grid(e->P, e->D, e->d_misc + 1, e->stream);
+    }
+    uint32_t collisions = 0;
+    CU(cudaMemcpyAsync(&collisions, e->d_misc + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    if (collisions) return engine_fail(e, EPI_ERR_STATE, "two agents on one cell (" + std::to_string(collisions) + " collisions)");
+    e->claim_dirty = true;
+    return EPI_OK;
+}
+
+void drop_graph(epi_engine* e) {
+    if (e->day_graph) {
+        cudaGraphExecDestroy(e->day_graph);
+        e->day_graph = nullptr;
+    }
+}
+
+// enqueue one simulated hour (kernels only).  `inject`: draws table already on device.
+// prev_was_sleep: the previous hour of this same call was a sleep hour that already ran k_sleep -> nothing to do.
+int enqueue_hour(epi_engine* e, uint32_t hour, uint32_t hour_offset, bool inject, bool skip_sleep) {
+    const uint32_t h = hour % 24u;
+    if (h >= 1 && h <= 6) {
+        if (skip_sleep) return EPI_OK;
+        Timed t(e, KK_SLEEP);
+        launch_sleep(e->P, e->D, hour_offset, e->stream);
+        return EPI_OK;
+    }
+    if (h == 0) {
+        cudaMemsetAsync(e->D.hosp_first, 0xFF, sizeof(uint32_t), e->stream);
+        Timed t(e, KK_SCAN);
+        launch_hospital_scan(e->P, e->D, e->stream);
+    }
+    {
+        Timed t(e, KK_HOUR);
+        launch_hour(e->P, e->D, hour_offset, inject, e->stream);
+    }
+    {
+        Timed t(e, KK_COMMIT);
+        launch_commit(e->P, e->D, hour_offset, e->stream);
+    }
+    return EPI_OK;
+}
+
+// claim stamps: stamp = hour - epoch_base + 1 must stay below 2^(32 - id_bits)
+int ensure_epoch(epi_engine* e, uint32_t first_hour, uint32_t last_hour) {
+    const uint64_t limit = 1ull << (32 - e->P.id_bits);
+    const bool fits = !e->claim_dirty && first_hour >= e->epoch_base && (uint64_t)(last_hour - e->epoch_base) + 1ull < limit;
+    if (!fits) {
+        CU(cudaMemsetAsync(e->D.claim, 0, n_cells(e) * sizeof(uint32_t), e->stream));
+        e->epoch_base = first_hour;
+        e->claim_dirty = false;
+    }
+    return EPI_OK;
+}
+
+int build_day_graph(epi_engine* e) {
+    // capture hours with h%24 = 1..23,0 (offsets 0..23) once; replayed for every aligned day
+    cudaGraph_t graph = nullptr;
+    const bool timing = e->timing;
+    e->timing = false;
+    const uint64_t launches0 = e->launches;
+    uint64_t kl0[EPI_N_KERNEL_KINDS];
+    memcpy(kl0, e->kernel_launches, sizeof(kl0));
+    CU(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+    bool sleep_done = false;
+    for (uint32_t off = 0; off < 24; ++off) {
+        const uint32_t hour = 1 + off;  // representative: only hour % 24 matters for the structure
+        const uint32_t h = hour % 24u;
+        const bool is_sleep = h >= 1 && h <= 6;
+        enqueue_hour(e, hour, off, false, is_sleep && sleep_done);
+        if (is_sleep) sleep_done = true;
+    }
+    cudaError_t r = cudaStreamEndCapture(e->stream, &graph);
+    e->timing = timing;
+    e->day_graph_launches = (uint32_t)(e->launches - launches0);
+    e->launches = launches0;
+    memcpy(e->kernel_launches, kl0, sizeof(kl0));
+    if (r != cudaSuccess) return engine_fail(e, EPI_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(r));
+    r = cudaGraphInstantiate(&e->day_graph, graph, 0);
+    cudaGraphDestroy(graph);
+    if (r != cudaSuccess) return engine_fail(e, EPI_ERR_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(r));
+    return EPI_OK;
+}
+
+void row_to_counts(const uint32_t* row, uint32_t hour, epi_counts* out) {
+    out->hour = hour;
+    out->susceptible = row[0]; out->exposed = row[1]; out->infected = row[2];
+    out->hospitalized = row[3]; out->recovered = row[4]; out->deceased = row[5];
+}
+
+// run hours [first, first+n) (n <= RING_ROWS), rows to out
+int run_chunk(epi_engine* e, uint32_t first_hour, uint32_t n, bool inject, epi_counts* out) {
+    CU(cudaMemsetAsync(e->D.counts, 0, (size_t)n * 8 * sizeof(uint32_t), e->stream));
+    int rc = ensure_epoch(e, first_hour, first_hour + n - 1);
+    if (rc) return rc;
+    std::vector<uint8_t> ran(n, 0);  // hour produced its own counts row
+    uint32_t off = 0;
+    bool sleep_done = false;  // a k_sleep already ran in the current run of consecutive sleep hours
+    while (off < n) {
+        const uint32_t hour = first_hour + off;
+        const bool aligned_day = !inject && !e->timing && e->graphs_enabled && hour % 24u == 1u && n - off >= 24u;
+        {
+            Timed t(e, KK_MISC);
+            launch_set_clock(e->d_clock, Clock{hour, e->epoch_base, first_hour, 0}, e->stream);
+        }
+        if (aligned_day) {
+            if (!e->day_graph) {
+                rc = build_day_graph(e);
+                if (rc) return rc;
+            }
+            CU(cudaGraphLaunch(e->day_graph, e->stream));
+            e->launches += e->day_graph_launches;
+            e->kernel_launches[KK_SLEEP] += 1; e->kernel_launches[KK_HOUR] += 18; e->kernel_launches[KK_COMMIT] += 18; e->kernel_launches[KK_SCAN] += 1;
+            for (uint32_t k = 0; k < 24; ++k) { const uint32_t h = (hour + k) % 24u; ran[off + k] = !(h >= 2 && h <= 6); }
+            off += 24;
+            sleep_done = false;
+            continue;
+        }
+        const uint32_t h = hour % 24u;
+        const bool is_sleep = h >= 1 && h <= 6;
+        rc = enqueue_hour(e, hour, 0, inject, is_sleep && sleep_done);
+        if (rc) return rc;
+        ran[off] = !(is_sleep && sleep_done);
+        sleep_done = is_sleep;
+        ++off;
+    }
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(e->h_counts, e->D.counts, (size_t)n * 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    if (e->timing) drain_events(e);
+    for (uint32_t k = 0; k < n; ++k) {
+        if (ran[k]) row_to_counts(e->h_counts + (size_t)k * 8, first_hour + k, &e->last_counts);
+        else e->last_counts.hour = first_hour + k;  // sleep hour: nothing observable changed (citizen/mod.rs:244-248)
+        out[k] = e->last_counts;
+        const uint64_t total = (uint64_t)out[k].susceptible + out[k].exposed + out[k].infected + out[k].hospitalized + out[k].recovered + out[k].deceased;
+        if (total != e->P.n)  // allocation_map.rs:128 assert_eq!(csv_record.total(), current_population)
+            return engine_fail(e, EPI_ERR_STATE, "counts total " + std::to_string(total) + " != population " + std::to_string(e->P.n) + " at hour " + std::to_string(first_hour + k));
+    }
+    return EPI_OK;
+}
+
+int upload_agents(epi_engine* e, const HostAgents& a) {
+    const size_t nb = (size_t)e->P.n * sizeof(uint32_t);
+    CU(cudaMemcpyAsync(e->D.cell, a.cell.data(), nb, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemcpyAsync(e->D.st, a.st.data(), nb, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemcpyAsync(e->D.t0, a.t0.data(), nb, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemcpyAsync(e->D.home, a.home.data(), nb, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemcpyAsync(e->D.work, a.work.data(), nb, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemcpyAsync(e->D.wsa, a.wsa.data(), nb, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return EPI_OK;
+}
+
+int snapshot_initial(epi_engine* e) {
+    const size_t nb = (size_t)e->P.n * sizeof(uint32_t);
+    CU(cudaMemcpyAsync(e->i_cell, e->D.cell, nb, cudaMemcpyDeviceToDevice, e->stream));
+    CU(cudaMemcpyAsync(e->i_st, e->D.st, nb, cudaMemcpyDeviceToDevice, e->stream));
+    CU(cudaMemcpyAsync(e->i_t0, e->D.t0, nb, cudaMemcpyDeviceToDevice, e->stream));
+    CU(cudaMemcpyAsync(e->i_home, e->D.home, nb, cudaMemcpyDeviceToDevice, e->stream));
+    CU(cudaMemcpyAsync(e->i_work, e->D.work, nb, cudaMemcpyDeviceToDevice, e->stream));
+    CU(cudaMemcpyAsync(e->i_wsa, e->D.wsa, nb, cudaMemcpyDeviceToDevice, e->stream));
+    return EPI_OK;
+}
+
+void initial_counts(epi_engine* e) {
+    const epi_config& c = e->cfg;
+    const uint32_t total = c.exposed + c.infected_mild_asymptomatic + c.infected_mild_symptomatic + c.infected_severe;
+    e->last_counts = epi_counts{0, c.number_of_agents - total, c.exposed, total - c.exposed, 0, 0, 0};
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* epi_version(void) { return "epirust_b200 0.1 (sm_100a)"; }
+
+const char* epi_last_error(const epi_engine* e) {
+    if (e) return e->err.c_str();
+    std::lock_guard<std::mutex> lk(g_err_mutex);
+    static thread_local std::string copy;
+    copy = g_err;
+    return copy.c_str();
+}
+
+int epi_create(const epi_config* cfg, uint64_t seed, int device, epi_engine** out) { return epi_create_region(cfg, seed, device, 0, out); }
+
+int epi_create_region(const epi_config* cfg, uint64_t seed, int device, int region, epi_engine** out) {
+    if (!cfg || !out) return engine_fail(nullptr, EPI_ERR_ARG, "null argument");
+    *out = nullptr;
+    const std::string bad = validate_config(*cfg);
+    if (!bad.empty()) return engine_fail(nullptr, EPI_ERR_CONFIG, bad);
+    if (region < 0 || region > 255) return engine_fail(nullptr, EPI_ERR_ARG, "region must be in 0..255");
+    int n_dev = 0;
+    cudaError_t cr = cudaGetDeviceCount(&n_dev);
+    if (cr != cudaSuccess || n_dev == 0)
+        return engine_fail(nullptr, EPI_ERR_CUDA, std::string("no CUDA device (there is no CPU fallback): ") + cudaGetErrorString(cr));
+    if (device < 0 || device >= n_dev) return engine_fail(nullptr, EPI_ERR_ARG, "device index out of range");
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    if (prop.major != 10)
+        return engine_fail(nullptr, EPI_ERR_CUDA, std::string("device ") + prop.name + " is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+                                                      "; this library is built for sm_100a only");
+    epi_engine* e = new epi_engine();
+    e->cfg = *cfg;
+    e->seed = seed;
+    e->device = device;
+    auto fail = [&](int rc) {
+        set_global_error(e->err);
+        epi_destroy(e);
+        return rc;
+    };
+    try {
+        e->geo = make_geometry(cfg->grid_size, cfg->number_of_agents, cfg->hospital_beds_percentage);
+        e->P = make_params(*cfg, e->geo, seed, region);
+        HostAgents agents;
+        build_population(*cfg, e->geo, seed, region, agents);
+        if (cudaSetDevice(device) != cudaSuccess) { e->err = "cudaSetDevice failed"; return fail(EPI_ERR_CUDA); }
+        if (cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) != cudaSuccess) { e->err = "cudaStreamCreate failed"; return fail(EPI_ERR_CUDA); }
+        e->stream = e->own_stream;
+        const size_t n = e->P.n, cells = n_cells(e);
+        bool ok = true;
+        ok &= dev_alloc(e, &e->D.cell, n) == cudaSuccess;
+        ok &= dev_alloc(e, &e->D.st, n) == cudaSuccess;
+        ok &= dev_alloc(e, &e->D.t0, n) == cudaSuccess;
+        ok &= dev_alloc(e, &e->D.home, n) == cudaSuccess;
+        ok &= dev_alloc(e, &e->D.work, n) == cudaSuccess;
+        ok &= dev_alloc(e, &e->D.wsa, n) == cudaSuccess;
+        ok &= dev_alloc(e, &e->D.prop, n) == cudaSuccess;
+        ok &= dev_alloc(e, &e->D.grid, cells + 4) == cudaSuccess;
+        ok &= dev_alloc(e, &e->D.claim, cells) == cudaSuccess;
+        ok &= dev_alloc(e, &e->D.counts, (size_t)RING_ROWS * 8) == cudaSuccess;
+        ok &= dev_alloc(e, &e->d_clock, 1) == cudaSuccess;
+        ok &= dev_alloc(e, &e->d_misc, 4) == cudaSuccess;
+        ok &= dev_alloc(e, &e->i_cell, n) == cudaSuccess;
+        ok &= dev_alloc(e, &e->i_st, n) == cudaSuccess;
+        ok &= dev_alloc(e, &e->i_t0, n) == cudaSuccess;
+        ok &= dev_alloc(e, &e->i_home, n) == cudaSuccess;
+        ok &= dev_alloc(e, &e->i_work, n) == cudaSuccess;
+        ok &= dev_alloc(e, &e->i_wsa, n) == cudaSuccess;
+        ok &= cudaMallocHost((void**)&e->h_counts, (size_t)RING_ROWS * 8 * sizeof(uint32_t)) == cudaSuccess;
+        if (!ok) { e->err = std::string("device allocation failed: ") + cudaGetErrorString(cudaGetLastError()); return fail(EPI_ERR_CUDA); }
+        e->D.hosp_first = e->d_misc;
+        e->D.clock = e->d_clock;
+        e->D.draws = nullptr;
+        int rc = upload_agents(e, agents);
+        if (rc) return fail(rc);
+        rc = snapshot_initial(e);
+        if (rc) return fail(rc);
+        rc = rebuild_grid(e);
+        if (rc) return fail(rc);
+        initial_counts(e);
+    } catch (const std::exception& ex) {
+        e->err = ex.what();
+        return fail(EPI_ERR_CONFIG);
+    }
+    *out = e;
+    return EPI_OK;
+}
+
+void epi_destroy(epi_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    drop_graph(e);
+    for (auto& pe : e->pending_events) { cudaEventDestroy(pe.second.first); cudaEventDestroy(pe.second.second); }
+    void* ptrs[] = {e->D.cell, e->D.st, e->D.t0, e->D.home, e->D.work, e->D.wsa, e->D.prop, e->D.grid, e->D.claim, e->D.counts,
+                    e->d_clock, e->d_misc, e->d_draws, e->i_cell, e->i_st, e->i_t0, e->i_home, e->i_work, e->i_wsa};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    if (e->h_counts) cudaFreeHost(e->h_counts);
+    if (e->own_stream) cudaStreamDestroy(e->own_stream);
+    delete e;
+}
+
+uint32_t epi_population(const epi_engine* e) { return e ? e->P.n : 0; }
+
+int epi_counts_at_start(const epi_engine* e, epi_counts* out) {
+    if (!e || !out) return engine_fail(e, EPI_ERR_ARG, "null argument");
+    const epi_config& c = e->cfg;
+    const uint32_t total = c.exposed + c.infected_mild_asymptomatic + c.infected_mild_symptomatic + c.infected_severe;
+    *out = epi_counts{0, c.number_of_agents - total, c.exposed, total - c.exposed, 0, 0, 0};
+    return EPI_OK;
+}
+
+int epi_set_stream(epi_engine* e, void* cuda_stream) {
+    if (!e) return engine_fail(e, EPI_ERR_ARG, "null engine");
+    CU(cudaSetDevice(e->device));
+    CU(cudaStreamSynchronize(e->stream));
+    drop_graph(e);
+    e->stream = cuda_stream ? (cudaStream_t)cuda_stream : e->own_stream;
+    return EPI_OK;
+}
+
+int epi_sync(epi_engine* e) {
+    if (!e) return engine_fail(e, EPI_ERR_ARG, "null engine");
+    CU(cudaSetDevice(e->device));
+    CU(cudaStreamSynchronize(e->stream));
+    return EPI_OK;
+}
+
+int epi_reset(epi_engine* e) {
+    if (!e) return engine_fail(e, EPI_ERR_ARG, "null engine");
+    CU(cudaSetDevice(e->device));
+    const size_t nb = (size_t)e->P.n * sizeof(uint32_t);
+    CU(cudaMemcpyAsync(e->D.cell, e->i_cell, nb, cudaMemcpyDeviceToDevice, e->stream));
+    CU(cudaMemcpyAsync(e->D.st, e->i_st, nb, cudaMemcpyDeviceToDevice, e->stream));
+    CU(cudaMemcpyAsync(e->D.t0, e->i_t0, nb, cudaMemcpyDeviceToDevice, e->stream));
+    CU(cudaMemcpyAsync(e->D.home, e->i_home, nb, cudaMemcpyDeviceToDevice, e->stream));
+    CU(cudaMemcpyAsync(e->D.work, e->i_work, nb, cudaMemcpyDeviceToDevice, e->stream));
+    CU(cudaMemcpyAsync(e->D.wsa, e->i_wsa, nb, cudaMemcpyDeviceToDevice, e->stream));
+    if (e->P.hospital_gen != 0) { e->P.hospital_gen = 0; drop_graph(e); }
+    initial_counts(e);
+    return rebuild_grid(e);
+}
+
+int epi_step(epi_engine* e, uint32_t hour, epi_counts* out) {
+    if (!e || !out) return engine_fail(e, EPI_ERR_ARG, "null argument");
+    CU(cudaSetDevice(e->device));
+    return run_chunk(e, hour, 1, false, out);
+}
+
+int epi_step_with_draws(epi_engine* e, uint32_t hour, const uint64_t* draws, epi_counts* out) {
+    if (!e || !out || !draws) return engine_fail(e, EPI_ERR_ARG, "null argument");
+    CU(cudaSetDevice(e->device));
+    const size_t count = (size_t)e->P.n * EPI_DRAWS_PER_AGENT;
+    if (e->draws_capacity < count) {
+        if (e->d_draws) cudaFree(e->d_draws);
+        e->d_draws = nullptr;
+        CU(dev_alloc(e, &e->d_draws, count));
+        e->draws_capacity = count;
+    }
+    CU(cudaMemcpyAsync(e->d_draws, draws, count * sizeof(uint64_t), cudaMemcpyHostToDevice, e->stream));
+    e->D.draws = e->d_draws;
+    const int rc = run_chunk(e, hour, 1, true, out);
+    e->D.draws = nullptr;
+    return rc;
+}
+
+int epi_run_hours(epi_engine* e, uint32_t first_hour, uint32_t n_hours, epi_counts* rows_out) {
+    if (!e || (!rows_out && n_hours)) return engine_fail(e, EPI_ERR_ARG, "null argument");
+    CU(cudaSetDevice(e->device));
+    uint32_t done = 0;
+    while (done < n_hours) {
+        const uint32_t n = std::min(n_hours - done, RING_ROWS);
+        const int rc = run_chunk(e, first_hour + done, n, false, rows_out + done);
+        if (rc) return rc;
+        done += n;
+    }
+    return EPI_OK;
+}
+
+int epi_lock_city(epi_engine* e) {
+    if (!e) return engine_fail(e, EPI_ERR_ARG, "null engine");
+    CU(cudaSetDevice(e->device));
+    { Timed t(e, KK_SWEEP); launch_lock(e->P, e->D, e->stream); }
+    CU(cudaGetLastError());
+    return EPI_OK;
+}
+int epi_unlock_city(epi_engine* e) {
+    if (!e) return engine_fail(e, EPI_ERR_ARG, "null engine");
+    CU(cudaSetDevice(e->device));
+    { Timed t(e, KK_SWEEP); launch_unlock(e->P, e->D, e->stream); }
+    CU(cudaGetLastError());
+    return EPI_OK;
+}
+int epi_vaccinate(epi_engine* e, double p, uint32_t hour) {
+    if (!e) return engine_fail(e, EPI_ERR_ARG, "null engine");
+    if (!(p >= 0.0 && p <= 1.0)) return engine_fail(e, EPI_ERR_ARG, "vaccination percentage out of [0,1]");  // gen_bool panics
+    CU(cudaSetDevice(e->device));
+    { Timed t(e, KK_SWEEP); launch_vaccinate(e->P, e->D, bernoulli_threshold(p), hour, e->stream); }
+    CU(cudaGetLastError());
+    return EPI_OK;
+}
+int epi_expand_hospital(epi_engine* e) {
+    if (!e) return engine_fail(e, EPI_ERR_ARG, "null engine");
+    CU(cudaSetDevice(e->device));
+    CU(cudaStreamSynchronize(e->stream));
+    if (e->P.hospital_gen != 1) { e->P.hospital_gen = 1; drop_graph(e); }
+    return EPI_OK;
+}
+
+int epi_get_state(epi_engine* e, int32_t* cx, int32_t* cy, uint32_t* st, uint32_t* t0, uint32_t* home, uint32_t* work, uint32_t* wsa) {
+    if (!e || !cx || !cy || !st || !t0 || !home || !work || !wsa) return engine_fail(e, EPI_ERR_ARG, "null argument");
+    CU(cudaSetDevice(e->device));
+    const size_t n = e->P.n, nb = n * sizeof(uint32_t);
+    std::vector<uint32_t> cell(n);
+    CU(cudaMemcpyAsync(cell.data(), e->D.cell, nb, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaMemcpyAsync(st, e->D.st, nb, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaMemcpyAsync(t0, e->D.t0, nb, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaMemcpyAsync(home, e->D.home, nb, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaMemcpyAsync(work, e->D.work, nb, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaMemcpyAsync(wsa, e->D.wsa, nb, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    for (size_t i = 0; i < n; ++i) {
+        cx[i] = (int32_t)(cell[i] & CELL_XMASK);
+        cy[i] = (int32_t)(cell[i] >> CELL_BITS);
+        // canonical form: fields that the reference's enum variant does not carry read as 0
+        const uint32_t state = st[i] & ST_STATE_MASK, sev = (st[i] >> ST_SEV_SHIFT) & 3u, ws = (st[i] >> ST_WS_SHIFT) & 3u;
+        if (!(state == ST_E || (state == ST_I && sev == SEV_PRE))) t0[i] = 0;
+        home[i] &= INDEX_MASK;
+        work[i] = ws == WS_NA ? 0u : (work[i] & INDEX_MASK);
+        if (ws != WS_STAFF) wsa[i] = 0;
+    }
+    return EPI_OK;
+}
+
+int epi_set_state(epi_engine* e, uint32_t n, const int32_t* cx, const int32_t* cy, const uint32_t* st, const uint32_t* t0, const uint32_t* home,
+                  const uint32_t* work, const uint32_t* wsa) {
+    if (!e || !cx || !cy || !st || !t0 || !home || !work || !wsa) return engine_fail(e, EPI_ERR_ARG, "null argument");
+    if (n != e->P.n) return engine_fail(e, EPI_ERR_ARG, "epi_set_state: n must equal epi_population()");
+    CU(cudaSetDevice(e->device));
+    HostAgents a;
+    a.resize(n);
+    for (uint32_t i = 0; i < n; ++i) {
+        if (cx[i] < 0 || cy[i] < 0 || (uint32_t)cx[i] >= e->geo.pitch || (uint32_t)cy[i] >= e->geo.rows)
+            return engine_fail(e, EPI_ERR_ARG, "epi_set_state: cell outside the grid");
+        const uint32_t ws = (st[i] >> ST_WS_SHIFT) & 3u;
+        if (home[i] >= e->geo.n_houses || (ws != WS_NA && work[i] >= e->geo.n_offices))
+            return engine_fail(e, EPI_ERR_ARG, "epi_set_state: house/office index out of range");
+        a.cell[i] = ((uint32_t)cy[i] << CELL_BITS) | (uint32_t)cx[i];
+        a.st[i] = st[i]; a.t0[i] = t0[i];
+        a.home[i] = home[i] | ((uint32_t)e->P.region << REGION_SHIFT);
+        a.work[i] = work[i] | ((uint32_t)e->P.region << REGION_SHIFT);
+        a.wsa[i] = wsa[i];
+    }
+    int rc = upload_agents(e, a);
+    if (rc) return rc;
+    return rebuild_grid(e);
+}
+
+int epi_geometry(const epi_engine* e, int32_t* out) {
+    if (!e || !out) return engine_fail(e, EPI_ERR_ARG, "null argument");
+    const Rect rs[4] = {e->geo.housing, e->geo.transport, e->geo.work, e->P.hospital[e->P.hospital_gen]};
+    for (int i = 0; i < 4; ++i) { out[4 * i] = rs[i].sx; out[4 * i + 1] = rs[i].sy; out[4 * i + 2] = rs[i].ex; out[4 * i + 3] = rs[i].ey; }
+    out[16] = (int32_t)e->geo.n_houses; out[17] = (int32_t)e->geo.n_offices; out[18] = e->geo.grid_size;
+    return EPI_OK;
+}
+
+int epi_get_grid(epi_engine* e, uint8_t* out, uint64_t capacity, uint32_t* pitch, uint32_t* rows) {
+    if (!e || !pitch || !rows) return engine_fail(e, EPI_ERR_ARG, "null argument");
+    *pitch = e->geo.pitch; *rows = e->geo.rows;
+    if (!out) return EPI_OK;
+    if (capacity < n_cells(e)) return engine_fail(e, EPI_ERR_ARG, "epi_get_grid: buffer too small");
+    CU(cudaSetDevice(e->device));
+    CU(cudaMemcpyAsync(out, e->D.grid, n_cells(e), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return EPI_OK;
+}
+
+int epi_set_kernel_timing(epi_engine* e, int on) {
+    if (!e) return engine_fail(e, EPI_ERR_ARG, "null engine");
+    CU(cudaSetDevice(e->device));
+    CU(cudaStreamSynchronize(e->stream));
+    drain_events(e);
+    e->timing = on != 0;
+    for (int k = 0; k < EPI_N_KERNEL_KINDS; ++k) { e->kernel_ms[k] = 0; e->kernel_launches[k] = 0; }
+    return EPI_OK;
+}
+int epi_get_kernel_times(epi_engine* e, double* ms_total, uint64_t* launches) {
+    if (!e || !ms_total || !launches) return engine_fail(e, EPI_ERR_ARG, "null argument");
+    CU(cudaSetDevice(e->device));
+    CU(cudaStreamSynchronize(e->stream));
+    drain_events(e);
+    for (int k = 0; k < EPI_N_KERNEL_KINDS; ++k) { ms_total[k] = e->kernel_ms[k]; launches[k] = e->kernel_launches[k]; }
+    return EPI_OK;
+}
+uint64_t epi_launch_count(const epi_engine* e, int reset) {
+    if (!e) return 0;
+    const uint64_t v = e->launches;
+    if (reset) const_cast<epi_engine*>(e)->launches = 0;
+    return v;
+}
+uint64_t epi_device_bytes(const epi_engine* e) { return e ? e->device_bytes : 0; }
+
+}  // extern "C"

@@ -1,0 +1,50 @@
+// One region engine: owns the HBM-resident state of a region and a CUDA stream; implements the C ABI of include/epi.h.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/epi.h"
+#include "host_model.h"
+#include "layout.h"
+
+struct epi_engine {
+    epi_config cfg{};
+    epi::Geometry geo{};
+    epi::Params P{};
+    epi::DevPtrs D{};
+    int device = 0;
+    uint64_t seed = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    // device allocations
+    epi::Clock* d_clock = nullptr;
+    uint32_t* d_misc = nullptr;  // [0] hosp_first, [1] collisions
+    uint64_t* d_draws = nullptr;
+    size_t draws_capacity = 0;
+    // snapshot of the initial agent state for epi_reset (device copies)
+    uint32_t *i_cell = nullptr, *i_st = nullptr, *i_t0 = nullptr, *i_home = nullptr, *i_work = nullptr, *i_wsa = nullptr;
+    uint32_t* h_counts = nullptr;  // pinned staging for the counts ring
+    uint64_t device_bytes = 0;
+    // claim stamping
+    uint32_t epoch_base = 0;
+    bool claim_dirty = true;  // claim array needs zeroing before next use
+    // day graph (hours h%24 = 1..23,0)
+    cudaGraphExec_t day_graph = nullptr;
+    uint32_t day_graph_launches = 0;
+    bool graphs_enabled = true;
+    // measurement
+    bool timing = false;
+    double kernel_ms[EPI_N_KERNEL_KINDS] = {0};
+    uint64_t kernel_launches[EPI_N_KERNEL_KINDS] = {0};
+    std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> pending_events;
+    uint64_t launches = 0;
+    epi_counts last_counts{};
+    mutable std::string err;
+};
+
+namespace epi {
+constexpr uint32_t RING_ROWS = 2400;  // counts ring: up to 100 simulated days between host synchronisations
+int engine_fail(const epi_engine* e, int code, const std::string& msg);
+void set_global_error(const std::string& msg);
+}  // namespace epi

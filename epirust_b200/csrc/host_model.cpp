@@ -1,0 +1,192 @@
+#include "host_model.h"
+
+#include <algorithm>
+#include <cmath>
+#include <stdexcept>
+#include <unordered_set>
+
+#include "philox.cuh"
+
+namespace epi {
+
+namespace {
+// init draw slots (domain DOM_INIT, hour word 0); see DESIGN.md "Draw slots"
+enum : uint32_t { IS_WORKING = 0, IS_PT = 1, IS_STAFF = 2, IS_IMMUNITY = 3, IS_ESSENTIAL = 4, IS_STARTX = 5, IS_STARTY = 6 };
+constexpr double kHospitalStaffPercentage = 0.002;  // models/constants.rs:43
+constexpr uint32_t kRoutineWorkTime = 8;            // models/constants.rs:32
+
+inline int ceil_frac(uint32_t g, double f) { return (int)std::ceil((double)g * f); }
+}  // namespace
+
+Geometry make_geometry(uint32_t grid_size, uint32_t n_agents, double beds_pct) {
+    // Vertical strips, 40 % housing / 20 % transport / 20 % work / 10 % hospital of the width, each G+1 rows tall
+    // because Area ends are inclusive and the reference passes grid_size as the end row (geography/mod.rs:43-50).
+    Geometry g;
+    g.grid_size = (int)grid_size;
+    const int G = (int)grid_size;
+    int x0 = 0;
+    auto strip = [&](double frac) {
+        const int w = ceil_frac(grid_size, frac);
+        Rect r{x0, 0, x0 + w - 1, G};
+        x0 += w;
+        return r;
+    };
+    g.housing = strip(0.4);
+    g.transport = strip(0.2);
+    g.work = strip(0.2);
+    g.hospital_initial = strip(0.1);
+    // area_factory: whole tiles only (geography/area.rs:95-117)
+    g.house_nx = (g.housing.ex - g.housing.sx + 1) / 2;
+    g.house_ny = (g.housing.ey - g.housing.sy + 1) / 2;
+    g.office_nx = (g.work.ex - g.work.sx + 1) / 10;
+    g.office_ny = (g.work.ey - g.work.sy + 1) / 10;
+    g.n_houses = (uint32_t)std::max(0, g.house_nx) * (uint32_t)std::max(0, g.house_ny);
+    g.n_offices = (uint32_t)std::max(0, g.office_nx) * (uint32_t)std::max(0, g.office_ny);
+    // Grid::resize_hospital (grid.rs:240-261): beds = ceil(N*beds% + N*staff%); shrink the strip to beds / (width-1) rows
+    // when the bed count fits in Area::get_number_of_cells (which is (ex-sx)*(ey-sy), area.rs:90-92)
+    g.hospital_resized = g.hospital_initial;
+    const uint32_t beds = (uint32_t)std::ceil((double)n_agents * beds_pct + (double)n_agents * kHospitalStaffPercentage);
+    const uint32_t dx = (uint32_t)(g.hospital_initial.ex - g.hospital_initial.sx);
+    const uint32_t cells = (uint32_t)((g.hospital_initial.ex - g.hospital_initial.sx) * (g.hospital_initial.ey - g.hospital_initial.sy));
+    if (beds <= cells && dx > 0) g.hospital_resized.ey = (int)(beds / dx);
+    // Grid::increase_hospital_size (grid.rs:233-238)
+    g.hospital_expanded = Rect{g.hospital_initial.sx, g.hospital_initial.sy, G, G};
+    const int max_x = std::max(std::max(g.hospital_initial.ex, g.hospital_expanded.ex), G);
+    g.pitch = (uint32_t)max_x + 1u;
+    g.pitch = (g.pitch + 3u) & ~3u;  // rows start on 4-byte boundaries (word-wise grid build)
+    g.rows = (uint32_t)G + 1u;
+    return g;
+}
+
+std::string validate_config(const epi_config& c) {
+    auto pct = [](double p) { return p >= 0.0 && p <= 1.0; };
+    if (c.number_of_agents == 0) return "population.Auto.number_of_agents must be > 0 (reference panics \"No citizens!\")";
+    if (c.grid_size < 10) return "geography_parameters.grid_size must be >= 10 (no offices otherwise)";
+    if (c.grid_size > MAX_COORD - 1) return "geography_parameters.grid_size must be <= 16382 (cell packing)";
+    if (!pct(c.public_transport_percentage) || !pct(c.working_percentage) || !pct(c.hospital_beds_percentage)) return "percentage out of [0,1]";
+    if (!pct(c.regular_transmission_rate) || !pct(c.high_transmission_rate) || !pct(c.death_rate) ||
+        !pct(c.percentage_asymptomatic_population) || !pct(c.percentage_severe_infected_population))
+        return "disease percentage out of [0,1]";
+    if (c.has_lockdown && !pct(c.essential_workers_population)) return "essential_workers_population out of [0,1]";
+    if (c.n_vaccinations < 0 || c.n_vaccinations > EPI_MAX_VACCINATIONS) return "too many Vaccinate interventions";
+    for (int i = 0; i < c.n_vaccinations; ++i)
+        if (!pct(c.vaccinate_percent[i])) return "Vaccinate.percent out of [0,1]";
+    const uint64_t infections = (uint64_t)c.exposed + c.infected_mild_asymptomatic + c.infected_mild_symptomatic + c.infected_severe;
+    if (infections > c.number_of_agents) return "more starting infections than agents (citizen_factory.rs:113-115)";
+    if (c.hours / 24u >= ST_DAY_MAX) return "hours too large for the 14-bit infection_day field";
+    if (c.number_of_agents > (1u << 27)) return "number_of_agents must be <= 2^27";
+    return "";
+}
+
+Params make_params(const epi_config& c, const Geometry& g, uint64_t seed, int region) {
+    Params P{};
+    P.n = c.number_of_agents;
+    P.grid_size = g.grid_size;
+    P.pitch = g.pitch;
+    P.rows = g.rows;
+    P.housing = g.housing; P.transport = g.transport; P.work = g.work;
+    P.hospital[0] = g.hospital_resized; P.hospital[1] = g.hospital_expanded;
+    P.hospital_gen = 0;
+    P.house_nx = g.house_nx; P.office_nx = g.office_nx;
+    P.regular_start = c.regular_transmission_start_day;
+    P.high_start = c.high_transmission_start_day;
+    P.last_day = c.last_day;
+    P.exposed_duration = c.exposed_duration;
+    P.pre_symptomatic_duration = c.pre_symptomatic_duration;
+    P.thr_rate[0] = 0;
+    P.thr_rate[1] = bernoulli_threshold(c.regular_transmission_rate);
+    P.thr_rate[2] = bernoulli_threshold(c.high_transmission_rate);
+    P.thr_death = bernoulli_threshold(c.death_rate);
+    P.thr_symptomatic = bernoulli_threshold(1.0 - c.percentage_asymptomatic_population);
+    P.thr_severe = bernoulli_threshold(c.percentage_severe_infected_population);
+    // Disease::is_to_be_hospitalized: current rate >= high rate (disease/mod.rs:97-99)
+    P.hospitalize_mask = (0.0 >= c.high_transmission_rate ? 1u : 0u) | (c.regular_transmission_rate >= c.high_transmission_rate ? 2u : 0u) | 4u;
+    uint32_t bits = 1;
+    while ((1ull << bits) < (uint64_t)P.n) ++bits;
+    P.id_bits = bits;
+    P.seed = seed;
+    P.region = region;
+    return P;
+}
+
+void build_population(const epi_config& c, const Geometry& g, uint64_t seed, int region, HostAgents& out) {
+    const uint32_t n = c.number_of_agents;
+    if (g.n_houses == 0 || g.n_offices == 0) throw std::runtime_error("grid too small: no houses or offices");
+    if ((uint64_t)n > 4ull * g.n_houses)
+        throw std::runtime_error("more than 4 agents per house: population does not fit the housing area (grid.rs:140-142)");
+    out.resize(n);
+    const uint64_t thr_working = bernoulli_threshold(c.working_percentage);
+    const uint64_t thr_pt = bernoulli_threshold(c.public_transport_percentage);
+    const uint64_t thr_staff = bernoulli_threshold(kHospitalStaffPercentage);
+    const uint64_t thr_essential = bernoulli_threshold(c.has_lockdown ? c.essential_workers_population : 0.0);
+    auto draw = [&](uint32_t agent, uint32_t slot) { return philox_draw(seed, agent, 0, DOM_INIT, slot); };
+
+    // Public-transport users are capped by the number of transport points Area::random_points can hand out
+    // (grid.rs:96-101 "fix the hack", area.rs:64-74): ceil(sqrt(n as f32)) columns x rows clipped to the strip.
+    const double want = (double)n * (c.public_transport_percentage + 0.1) * (c.working_percentage + 0.1);
+    const size_t want_points = (size_t)std::ceil(want);
+    const size_t side = (size_t)std::ceil(std::sqrt((float)want_points));
+    const size_t tw = (size_t)(g.transport.ex - g.transport.sx + 1), th = (size_t)(g.transport.ey - g.transport.sy + 1);
+    const size_t pt_capacity = std::min(want_points, std::min(side, tw) * std::min(side, th));
+
+    size_t pt_users = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        const bool working = bernoulli(draw(i, IS_WORKING), thr_working);
+        const bool pt = bernoulli(draw(i, IS_PT), thr_pt) && working && pt_users < pt_capacity;
+        if (pt) ++pt_users;
+        uint32_t ws = WS_NA;
+        if (working) {
+            ws = bernoulli(draw(i, IS_STAFF), thr_staff) ? WS_STAFF : WS_NORMAL;
+            if (ws == WS_NORMAL && bernoulli(draw(i, IS_ESSENTIAL), thr_essential)) ws = WS_ESSENTIAL;
+        }
+        const uint32_t immunity_plus2 = (uint32_t)mulhi64(draw(i, IS_IMMUNITY), 5);
+        out.st[i] = ST_S | (immunity_plus2 << ST_IMM_SHIFT) | (pt ? ST_PT : 0u) | (ws << ST_WS_SHIFT) | (AK_HOME << ST_AREA_SHIFT);
+        out.t0[i] = 0;
+        out.home[i] = (i % g.n_houses) | ((uint32_t)region << REGION_SHIFT);
+        out.work[i] = working ? ((i % g.n_offices) | ((uint32_t)region << REGION_SHIFT)) : 0u;
+        out.wsa[i] = ws == WS_STAFF ? kRoutineWorkTime : 0u;
+    }
+
+    // starting infections: uniform without replacement, then exposed / asymptomatic / mild / severe in that order
+    const uint32_t total = c.exposed + c.infected_mild_asymptomatic + c.infected_mild_symptomatic + c.infected_severe;
+    std::vector<uint32_t> chosen;
+    chosen.reserve(total);
+    std::unordered_set<uint32_t> seen;
+    for (uint32_t k = 0; chosen.size() < total; ++k) {
+        const uint32_t idx = (uint32_t)mulhi64(philox_draw(seed, k, 0, DOM_STARTINF, 0), n);
+        if (seen.insert(idx).second) chosen.push_back(idx);
+    }
+    size_t q = 0;
+    auto infect = [&](uint32_t count, uint32_t state, uint32_t sev, uint32_t day) {
+        for (uint32_t j = 0; j < count; ++j) {
+            uint32_t& s = out.st[chosen[q++]];
+            s = (s & ~ST_STATE_MASK) | state | (sev << ST_SEV_SHIFT) | (day << ST_DAY_SHIFT);
+        }
+    };
+    infect(c.exposed, ST_E, 0, 0);  // Exposed { at_hour: 0 }
+    infect(c.infected_mild_asymptomatic, ST_I, SEV_ASYM, 1);
+    infect(c.infected_mild_symptomatic, ST_I, SEV_MILD, 1);
+    infect(c.infected_severe, ST_I, SEV_SEVERE, 1);
+
+    // start cells: agent i lives in house i % H together with i+H, i+2H, ...; the k housemates take the first k of
+    // (sx,sy),(sx,sy+1),(sx+1,sy),(sx+1,sy+1); a lone occupant gets a uniformly random corner (area.rs:64-74)
+    const uint32_t H = g.n_houses;
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint32_t house = i % H;
+        const uint32_t housemates = (n - 1 - house) / H + 1;  // agents house, house+H, ... < n
+        const uint32_t rank = i / H;
+        const int sx = g.housing.sx + 2 * (int)(house % (uint32_t)g.house_nx);
+        const int sy = g.housing.sy + 2 * (int)(house / (uint32_t)g.house_nx);
+        int x, y;
+        if (housemates == 1) {
+            x = sx + (int)mulhi64(draw(i, IS_STARTX), 2);
+            y = sy + (int)mulhi64(draw(i, IS_STARTY), 2);
+        } else {
+            x = sx + (int)(rank / 2);
+            y = sy + (int)(rank % 2);
+        }
+        out.cell[i] = ((uint32_t)y << CELL_BITS) | (uint32_t)x;
+    }
+}
+
+}  // namespace epi

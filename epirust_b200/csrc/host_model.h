@@ -1,0 +1,41 @@
+// Host-side model set-up of one region: geography and the Auto population factory, producing the structure-of-arrays
+// image that is uploaded to HBM once.  Product code (the oracle has its own independent restatement).
+#pragma once
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/epi.h"
+#include "layout.h"
+
+namespace epi {
+
+struct Geometry {
+    int grid_size = 0;
+    Rect housing{}, transport{}, work{}, hospital_initial{}, hospital_resized{}, hospital_expanded{};
+    int house_nx = 0, house_ny = 0, office_nx = 0, office_ny = 0;
+    uint32_t n_houses = 0, n_offices = 0;
+    uint32_t pitch = 0, rows = 0;
+};
+
+// geography::define_geography + Grid::resize_hospital (geography/mod.rs:33-70, grid.rs:240-261)
+Geometry make_geometry(uint32_t grid_size, uint32_t n_agents, double hospital_beds_percentage);
+
+struct HostAgents {
+    std::vector<uint32_t> cell, st, t0, home, work, wsa;
+    size_t size() const { return st.size(); }
+    void resize(size_t n) { cell.resize(n); st.resize(n); t0.resize(n); home.resize(n); work.resize(n); wsa.resize(n); }
+};
+
+// Grid::generate_population + citizen_factory + set_starting_infections + init_interventions' essential workers
+// (grid.rs:83-155, citizen_factory.rs:31-134, epidemiology_simulation.rs:178-192).  Throws std::runtime_error.
+void build_population(const epi_config& cfg, const Geometry& geo, uint64_t seed, int region, HostAgents& out);
+
+// Params for the kernels from config + geometry
+Params make_params(const epi_config& cfg, const Geometry& geo, uint64_t seed, int region);
+
+// validation of what the reference would panic on later (and our own packing limits)
+std::string validate_config(const epi_config& cfg);
+
+}  // namespace epi

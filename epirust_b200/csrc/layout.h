@@ -1,0 +1,99 @@
+// Device data layout of one region engine.  Everything here is resident in HBM for the whole run.
+//
+// Per agent (structure of arrays, index = agent id = creation order, engine/src/citizen/citizen_factory.rs:44-47):
+//   cell[N] u32   packed (y << 14) | x of the cell the agent stands on          (reference: the map key Point)
+//   st[N]   u32   packed Citizen fields, layout below                          (citizen/mod.rs:48-63)
+//   t0[N]   u32   at_hour of State::Exposed / Severity::Pre                     (state_machine/state.rs:22-37)
+//   home[N] u32   house index  | home region << 24                             (Citizen.home_location)
+//   work[N] u32   office index | work region << 24 (unused for WorkStatus::NA)  (Citizen.work_location)
+//   wsa[N]  u32   WorkStatus::HospitalStaff.work_start_at (0.14 % of agents)    (citizen/work_status.rs:26)
+//   prop[N] u32   this hour's proposal, hour kernel -> commit kernel
+// Per cell (pitch = grid_size + 1 columns, rows = grid_size + 1; y-major so x neighbours are adjacent bytes):
+//   grid[cells]  u8   0 vacant, 1 occupied & not infectious, 2 occupied & regular-rate, 3 occupied & high-rate
+//                     (replaces AgentLocationMap / FnvHashMap<Point, Citizen>, allocation_map.rs:44-49: vacancy and
+//                      the neighbour's transmission rate are the only things other agents read from a cell)
+//   claim[cells] u32  (stamp << id_bits) | (id_mask - agent id), atomicMax: lowest agent id wins the cell this hour
+#pragma once
+#include <stdint.h>
+
+namespace epi {
+
+// ---- agent state word ------------------------------------------------------------------------------------------
+enum : uint32_t {
+    ST_S = 0, ST_E = 1, ST_I = 2, ST_R = 3, ST_D = 4,               // state_machine/state.rs:31-37
+    SEV_PRE = 0, SEV_ASYM = 1, SEV_MILD = 2, SEV_SEVERE = 3,         // state_machine/state.rs:22-28
+    WS_NORMAL = 0, WS_ESSENTIAL = 1, WS_STAFF = 2, WS_NA = 3,        // citizen/work_status.rs:22-28
+    AK_HOME = 0, AK_WORK = 1, AK_TRANSPORT = 2, AK_HOUSING = 3, AK_HOSPITAL0 = 4, AK_HOSPITAL1 = 5,  // Citizen.current_area
+};
+constexpr uint32_t ST_STATE_MASK = 0x7u;
+constexpr int ST_SEV_SHIFT = 3;        // 2 bits
+constexpr int ST_IMM_SHIFT = 5;        // 3 bits, immunity + 2
+constexpr uint32_t ST_VACC = 1u << 8;  // vaccinated
+constexpr uint32_t ST_PT = 1u << 9;    // uses_public_transport
+constexpr uint32_t ST_HOSP = 1u << 10; // hospitalized
+constexpr uint32_t ST_ISO = 1u << 11;  // isolated
+constexpr uint32_t ST_WQ = 1u << 12;   // work_quarantined
+constexpr int ST_WS_SHIFT = 13;        // 2 bits
+constexpr int ST_AREA_SHIFT = 15;      // 3 bits
+constexpr uint32_t ST_AREA_MASK = 7u << ST_AREA_SHIFT;
+constexpr int ST_DAY_SHIFT = 18;       // 14 bits infection_day
+constexpr uint32_t ST_DAY_MAX = 0x3FFFu;
+
+// ---- cell packing ---------------------------------------------------------------------------------------------------
+constexpr int CELL_BITS = 14;
+constexpr uint32_t CELL_XMASK = (1u << CELL_BITS) - 1;
+constexpr uint32_t MAX_COORD = CELL_XMASK;  // grid_size <= 16382
+
+// ---- proposal word ----------------------------------------------------------------------------------------------------
+constexpr uint32_t PROP_CELL_MASK = (1u << 28) - 1;
+constexpr uint32_t PROP_MOVE = 1u << 28;   // agent wants to move to bits 0..27
+constexpr uint32_t PROP_DIRTY = 1u << 29;  // the agent's grid byte changed
+constexpr int PROP_BYTE_SHIFT = 30;        // new grid byte - 1
+
+constexpr uint32_t HOSP_NONE = 0xFFFFFFFFu;
+constexpr uint32_t REGION_SHIFT = 24;
+constexpr uint32_t INDEX_MASK = (1u << REGION_SHIFT) - 1;
+
+struct Rect {
+    int sx, sy, ex, ey;  // inclusive on both ends (geography/area.rs:83-88)
+};
+
+// run constants, passed by value to every kernel
+struct Params {
+    uint32_t n;        // agents
+    int grid_size;     // G: is_point_in_grid is 0 <= x,y < G (allocation_map.rs:156-159)
+    uint32_t pitch;    // bytes per grid row
+    uint32_t rows;
+    Rect housing, transport, work;  // geography/mod.rs:33-70
+    Rect hospital[2];               // [0] after Grid::resize_hospital, [1] after increase_hospital_size
+    int hospital_gen;               // which one is grid.hospital_area now
+    int house_nx, office_nx;        // houses / offices per row (area_factory, geography/area.rs:95-117)
+    // disease (common/src/disease/mod.rs:26-45)
+    uint32_t regular_start, high_start, last_day;
+    uint32_t exposed_duration, pre_symptomatic_duration;
+    uint64_t thr_rate[3];  // Bernoulli thresholds for rate class 0 (never), 1 (regular), 2 (high)
+    uint64_t thr_death, thr_symptomatic, thr_severe;
+    uint32_t hospitalize_mask;  // bit c set: rate class c satisfies Disease::is_to_be_hospitalized (disease/mod.rs:97-99)
+    uint32_t id_bits;           // claim word: low id_bits = id_mask - agent
+    uint64_t seed;
+    int region;
+};
+
+struct Clock {           // device-resident so CUDA graphs can be replayed for any day
+    uint32_t hour_base;  // kernels run hour = hour_base + offset
+    uint32_t epoch_base; // claim stamp = hour - epoch_base + 1
+    uint32_t ring_base;  // Counts of `hour` accumulate in counts ring row hour - ring_base
+    uint32_t pad;
+};
+
+struct DevPtrs {
+    uint32_t *cell, *st, *t0, *home, *work, *wsa, *prop;
+    uint8_t* grid;
+    uint32_t* claim;
+    uint32_t* counts;      // ring [rows][8]: S,E,I,H,R,D,pad,pad
+    uint32_t* hosp_first;  // rank of the first vacant hospital cell in Area::iter order, or HOSP_NONE
+    const Clock* clock;
+    const uint64_t* draws; // injected draws table or nullptr
+};
+
+}  // namespace epi

@@ -1,0 +1,266 @@
+#include "simulation.h"
+
+#include <sys/stat.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <ctime>
+#include <fstream>
+
+#include "engine.h"
+#include "json.h"
+
+namespace epi {
+
+void Listeners::simulation_ended(const std::string& base) const {
+    {
+        // csv crate `Writer::serialize(Counts)`: header row from the field names, '\n' terminated (counts.rs:25-34)
+        std::ofstream f(base + ".csv");
+        if (!f) throw std::runtime_error("Failed to write to file " + base + ".csv");
+        f << "hour,susceptible,exposed,infected,hospitalized,recovered,deceased\n";
+        for (const epi_counts& c : counts)
+            f << c.hour << ',' << c.susceptible << ',' << c.exposed << ',' << c.infected << ',' << c.hospitalized << ',' << c.recovered << ',' << c.deceased
+              << '\n';
+    }
+    {
+        // serde_json::to_writer(Vec<InterventionReport>): compact, field order hour, intervention, data
+        std::ofstream f(base + "_interventions.json");
+        if (!f) throw std::runtime_error("Failed to create intervention report file");
+        f << '[';
+        for (size_t i = 0; i < interventions.size(); ++i) {
+            if (i) f << ',';
+            f << "{\"hour\":" << interventions[i].hour << ",\"intervention\":\"" << interventions[i].intervention << "\",\"data\":" << interventions[i].data << '}';
+        }
+        f << ']';
+    }
+}
+
+std::string output_file_format(const std::string& output_dir, const std::string& engine_id) {
+    const std::string dir = output_dir + "/output";
+    mkdir(output_dir.c_str(), 0755);
+    mkdir(dir.c_str(), 0755);
+    char stamp[32];
+    const std::time_t now = std::time(nullptr);
+    std::tm tm_utc;
+    gmtime_r(&now, &tm_utc);
+    std::strftime(stamp, sizeof(stamp), "%Y-%m-%dT%H:%M:%S", &tm_utc);
+    return dir + "/simulation_" + engine_id + "_" + stamp;
+}
+
+static void log_counts(const epi_counts& c) {
+    std::printf("INFO - S: %u, E:%u, I: %u, H: %u, R: %u, D: %u\n", c.susceptible, c.exposed, c.infected, c.hospitalized, c.recovered, c.deceased);
+}
+
+int run_single_engine(epi_engine* e, const epi_config& cfg, RunResult& result, bool log) {
+    LockdownIntervention lockdown(cfg);
+    BuildNewHospital build_new_hospital(cfg);
+    VaccinateIntervention vaccinate(cfg);
+    Listeners listeners;
+    epi_counts counts_at_hr;
+    int rc = epi_counts_at_start(e, &counts_at_hr);
+    if (rc) return rc;
+    if (log) log_counts(counts_at_hr);
+    const auto start_time = std::chrono::steady_clock::now();
+    auto elapsed = [&] { return std::chrono::duration<double>(std::chrono::steady_clock::now() - start_time).count(); };
+    std::vector<epi_counts> seg;
+    bool stop = false;
+    uint32_t simulation_hour = 1;
+    while (simulation_hour < cfg.hours && !stop) {
+        // Run up to (and including) the next hour at which a host decision can change device state:
+        // start of day (lockdown.rs:55, hospital.rs:55,70), a configured vaccination hour (vaccination.rs:52),
+        // the unlock hour (lockdown.rs:69-73).  The per-hour stop rule only needs the Counts rows.
+        uint32_t seg_end = (simulation_hour + 23u) / 24u * 24u;
+        seg_end = std::min(seg_end, vaccinate.next_hour(simulation_hour));
+        if (lockdown.is_locked_down() && lockdown.unlock_hour() >= simulation_hour) seg_end = std::min(seg_end, lockdown.unlock_hour());
+        seg_end = std::min(seg_end, cfg.hours - 1u);
+        const uint32_t n = seg_end - simulation_hour + 1u;
+        seg.resize(n);
+        rc = epi_run_hours(e, simulation_hour, n, seg.data());
+        if (rc) return rc;
+        for (uint32_t k = 0; k < n && !stop; ++k) {
+            counts_at_hr = seg[k];  // counts_at_hr.increment_hour() + simulate()
+            listeners.counts_updated(counts_at_hr);
+            // CitizenLocationMap::process_interventions (allocation_map.rs:306-337)
+            if (const double* pct = vaccinate.get_vaccination_percentage(counts_at_hr)) {
+                if (log) std::printf("INFO - Vaccination\n");
+                rc = epi_vaccinate(e, *pct, counts_at_hr.hour);
+                if (rc) return rc;
+                listeners.intervention_applied(counts_at_hr.hour, vaccinate.name(), vaccinate.json_data());
+            }
+            if (lockdown.should_apply(counts_at_hr)) {
+                lockdown.apply();
+                if (log) std::printf("INFO - Locking the city. Hour: %u\n", counts_at_hr.hour);
+                rc = epi_lock_city(e);
+                if (rc) return rc;
+                listeners.intervention_applied(counts_at_hr.hour, lockdown.name(), lockdown.json_data());
+            }
+            if (lockdown.should_unlock(counts_at_hr)) {
+                if (log) std::printf("INFO - Unlocking city. Hour: %u\n", counts_at_hr.hour);
+                rc = epi_unlock_city(e);
+                if (rc) return rc;
+                lockdown.unapply();
+                listeners.intervention_applied(counts_at_hr.hour, lockdown.name(), lockdown.json_data());
+            }
+            build_new_hospital.counts_updated(counts_at_hr);
+            if (build_new_hospital.should_apply(counts_at_hr)) {
+                if (log) std::printf("INFO - Increasing the hospital size\n");
+                rc = epi_expand_hospital(e);
+                if (rc) return rc;
+                build_new_hospital.apply();
+                listeners.intervention_applied(counts_at_hr.hour, build_new_hospital.name(), build_new_hospital.json_data());
+            }
+            // Epidemiology::stop_simulation, Standalone arm (epidemiology_simulation.rs:564-575)
+            if (counts_at_hr.exposed == 0 && counts_at_hr.infected == 0 && counts_at_hr.hospitalized == 0) stop = true;
+            if (!stop && counts_at_hr.hour % 100u == 0 && log) {
+                std::printf("INFO - Throughput: %f iterations/sec; simulation hour %u of %u\n", (double)counts_at_hr.hour / elapsed(), counts_at_hr.hour, cfg.hours);
+                log_counts(counts_at_hr);
+            }
+        }
+        simulation_hour = seg_end + 1u;
+    }
+    result.loop_seconds = elapsed();
+    if (log) {
+        std::printf("INFO - Number of iterations: %u, Total Time taken %f seconds\n", counts_at_hr.hour, result.loop_seconds);
+        std::printf("INFO - Iterations/sec: %f\n", (double)counts_at_hr.hour / result.loop_seconds);
+        std::printf("INFO - Agent-steps/sec: %e\n", (double)counts_at_hr.hour * (double)cfg.number_of_agents / result.loop_seconds);
+    }
+    result.rows = std::move(listeners.counts);
+    result.interventions = std::move(listeners.interventions);
+    return EPI_OK;
+}
+
+// ---- config JSON (common::config::Config, common/src/config/mod.rs:44-58) ------------------------------------------
+static void config_from_value(const JsonValue& root, epi_config& c) {
+    std::memset(&c, 0, sizeof(c));
+    const JsonValue& pop = root.at("population");
+    if (const JsonValue* a = pop.find("Auto")) {
+        c.number_of_agents = a->at("number_of_agents").as_u32("number_of_agents");
+        c.public_transport_percentage = a->at("public_transport_percentage").as_number("public_transport_percentage");
+        c.working_percentage = a->at("working_percentage").as_number("working_percentage");
+    } else if (pop.find("Csv")) {
+        throw std::runtime_error("population.Csv is not supported by the GPU engine yet (SURVEY.md section 8f row 3); use population.Auto");
+    } else {
+        throw std::runtime_error("unknown variant for `population`, expected `Csv` or `Auto`");
+    }
+    const JsonValue* dis = root.find("disease");
+    if (!dis || dis->kind == JsonValue::Null) throw std::runtime_error("`disease` is required (Config::get_disease unwraps it, common/src/config/mod.rs:83-85)");
+    c.regular_transmission_start_day = dis->at("regular_transmission_start_day").as_u32("regular_transmission_start_day");
+    c.high_transmission_start_day = dis->at("high_transmission_start_day").as_u32("high_transmission_start_day");
+    c.last_day = dis->at("last_day").as_u32("last_day");
+    c.asymptomatic_last_day = dis->at("asymptomatic_last_day").as_u32("asymptomatic_last_day");
+    c.mild_infected_last_day = dis->at("mild_infected_last_day").as_u32("mild_infected_last_day");
+    c.regular_transmission_rate = dis->at("regular_transmission_rate").as_number("regular_transmission_rate");
+    c.high_transmission_rate = dis->at("high_transmission_rate").as_number("high_transmission_rate");
+    c.death_rate = dis->at("death_rate").as_number("death_rate");
+    c.percentage_asymptomatic_population = dis->at("percentage_asymptomatic_population").as_number("percentage_asymptomatic_population");
+    c.percentage_severe_infected_population = dis->at("percentage_severe_infected_population").as_number("percentage_severe_infected_population");
+    c.exposed_duration = dis->at("exposed_duration").as_u32("exposed_duration");
+    c.pre_symptomatic_duration = dis->at("pre_symptomatic_duration").as_u32("pre_symptomatic_duration");
+    const JsonValue& geo = root.at("geography_parameters");
+    c.grid_size = geo.at("grid_size").as_u32("grid_size");
+    c.hospital_beds_percentage = geo.at("hospital_beds_percentage").as_number("hospital_beds_percentage");
+    c.hours = root.at("hours").as_u32("hours");
+    const JsonValue& ivs = root.at("interventions");
+    if (ivs.kind != JsonValue::Array) throw std::runtime_error("`interventions` must be an array");
+    for (const JsonValue& iv : ivs.arr) {
+        if (iv.kind != JsonValue::Object || iv.obj.size() != 1) throw std::runtime_error("each intervention must be an object with one variant key");
+        const std::string& variant = iv.obj[0].first;
+        const JsonValue& body = iv.obj[0].second;
+        if (variant == "Vaccinate") {
+            if (c.n_vaccinations >= EPI_MAX_VACCINATIONS) throw std::runtime_error("too many Vaccinate interventions (max 8)");
+            // later entries with the same hour overwrite (vaccination.rs:43-45)
+            const uint32_t at_hour = body.at("at_hour").as_u32("at_hour");
+            const double percent = body.at("percent").as_number("percent");
+            int slot = c.n_vaccinations;
+            for (int i = 0; i < c.n_vaccinations; ++i)
+                if (c.vaccinate_at_hour[i] == at_hour) slot = i;
+            c.vaccinate_at_hour[slot] = at_hour;
+            c.vaccinate_percent[slot] = percent;
+            if (slot == c.n_vaccinations) c.n_vaccinations++;
+        } else if (variant == "Lockdown") {
+            if (!c.has_lockdown) {  // .next(): the first one wins (lockdown.rs:34-44)
+                c.has_lockdown = 1;
+                c.lockdown_at_number_of_infections = body.at("at_number_of_infections").as_u32("at_number_of_infections");
+                c.essential_workers_population = body.at("essential_workers_population").as_number("essential_workers_population");
+            }
+        } else if (variant == "BuildNewHospital") {
+            if (!c.has_build_new_hospital) {
+                c.has_build_new_hospital = 1;
+                c.spread_rate_threshold = body.at("spread_rate_threshold").as_u32("spread_rate_threshold");
+            }
+        } else {
+            throw std::runtime_error("unknown variant `" + variant + "`, expected one of `Vaccinate`, `Lockdown`, `BuildNewHospital`");
+        }
+    }
+    if (const JsonValue* si = root.find("starting_infections")) {
+        c.infected_mild_asymptomatic = si->at("infected_mild_asymptomatic").as_u32("infected_mild_asymptomatic");
+        c.infected_mild_symptomatic = si->at("infected_mild_symptomatic").as_u32("infected_mild_symptomatic");
+        c.infected_severe = si->at("infected_severe").as_u32("infected_severe");
+        c.exposed = si->at("exposed").as_u32("exposed");
+    } else {
+        c.exposed = 1;  // StartingInfections::default (starting_infections.rs:65-69)
+    }
+}
+
+}  // namespace epi
+
+using namespace epi;
+
+extern "C" {
+
+int epi_config_from_json_string(const char* json_text, epi_config* out) {
+    if (!json_text || !out) return engine_fail(nullptr, EPI_ERR_ARG, "null argument");
+    try {
+        config_from_value(json_parse(json_text), *out);
+    } catch (const std::exception& ex) {
+        return engine_fail(nullptr, EPI_ERR_CONFIG, ex.what());
+    }
+    return EPI_OK;
+}
+
+int epi_config_from_json(const char* json_path, epi_config* out) {
+    if (!json_path || !out) return engine_fail(nullptr, EPI_ERR_ARG, "null argument");
+    std::string text;
+    try {
+        text = json_read_file(json_path);
+    } catch (const std::exception& ex) {
+        return engine_fail(nullptr, EPI_ERR_IO, ex.what());
+    }
+    return epi_config_from_json_string(text.c_str(), out);
+}
+
+int epi_run_standalone(const epi_config* cfg, uint64_t seed, int device, const char* output_dir, const char* engine_id, epi_counts* rows_out,
+                       uint32_t max_rows, uint32_t* n_rows, double* loop_seconds) {
+    if (!cfg) return engine_fail(nullptr, EPI_ERR_ARG, "null config");
+    epi_engine* e = nullptr;
+    int rc = epi_create(cfg, seed, device, &e);
+    if (rc) return rc;
+    RunResult res;
+    const bool log = std::getenv("EPI_LOG") != nullptr;
+    rc = run_single_engine(e, *cfg, res, log);
+    if (rc) {
+        set_global_error(e->err);
+        epi_destroy(e);
+        return rc;
+    }
+    epi_destroy(e);
+    if (output_dir) {
+        try {
+            Listeners l;
+            l.counts = res.rows;
+            l.interventions = res.interventions;
+            l.simulation_ended(output_file_format(output_dir, engine_id ? engine_id : "0"));
+        } catch (const std::exception& ex) {
+            return engine_fail(nullptr, EPI_ERR_IO, ex.what());
+        }
+    }
+    if (n_rows) *n_rows = (uint32_t)res.rows.size();
+    if (loop_seconds) *loop_seconds = res.loop_seconds;
+    if (rows_out)
+        for (uint32_t i = 0; i < std::min<uint32_t>(max_rows, (uint32_t)res.rows.size()); ++i) rows_out[i] = res.rows[i];
+    return EPI_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,211 @@
+"""Python mirror of the region engine over the C ABI (tests, bench and the torchrun launcher use this).
+
+The class and method names follow the reference's own vocabulary (CitizenLocationMap::simulate, lock_city,
+vaccinate ...; engine/src/allocation_map.rs) so the parity tests read like the reference's tests.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _ffi
+from ._ffi import EpiConfig, EpiCounts
+
+STATE_FIELDS = ("cell_x", "cell_y", "st", "t0", "home", "work", "wsa")
+STATE_DTYPES = (np.int32, np.int32, np.uint32, np.uint32, np.uint32, np.uint32, np.uint32)
+COUNT_FIELDS = ("hour", "susceptible", "exposed", "infected", "hospitalized", "recovered", "deceased")
+
+# the `disease` block of the reference's engine/config/default.json
+DEFAULT_DISEASE = dict(
+    regular_transmission_start_day=5, high_transmission_start_day=6, last_day=26,
+    asymptomatic_last_day=9, mild_infected_last_day=12,
+    regular_transmission_rate=0.25, high_transmission_rate=0.25, death_rate=0.035,
+    percentage_asymptomatic_population=0.3, percentage_severe_infected_population=0.3,
+    exposed_duration=48, pre_symptomatic_duration=48,
+)
+
+
+def make_config(n_agents=10000, grid_size=250, hours=1080, exposed=1, asym=0, mild=0, severe=0,
+                pt=0.2, working=0.7, beds=0.003, lockdown=None, hospital=None, vaccinate=(), **disease):
+    """Build an EpiConfig; defaults are engine/config/default.json without its Lockdown intervention."""
+    c = EpiConfig()
+    c.number_of_agents = n_agents
+    c.public_transport_percentage = pt
+    c.working_percentage = working
+    d = dict(DEFAULT_DISEASE)
+    d.update(disease)
+    for k, v in d.items():
+        setattr(c, k, v)
+    c.grid_size = grid_size
+    c.hospital_beds_percentage = beds
+    c.hours = hours
+    c.exposed, c.infected_mild_asymptomatic, c.infected_mild_symptomatic, c.infected_severe = exposed, asym, mild, severe
+    if lockdown is not None:
+        c.has_lockdown = 1
+        c.lockdown_at_number_of_infections, c.essential_workers_population = lockdown
+    if hospital is not None:
+        c.has_build_new_hospital = 1
+        c.spread_rate_threshold = hospital
+    c.n_vaccinations = len(vaccinate)
+    for i, (h, p) in enumerate(vaccinate):
+        c.vaccinate_at_hour[i] = h
+        c.vaccinate_percent[i] = p
+    return c
+
+
+def config_from_json(path):
+    L = _ffi.load()
+    c = EpiConfig()
+    if L.epi_config_from_json(str(path).encode(), C.byref(c)):
+        raise ValueError(L.epi_last_error(None).decode())
+    return c
+
+
+def config_from_json_string(text):
+    L = _ffi.load()
+    c = EpiConfig()
+    if L.epi_config_from_json_string(text.encode(), C.byref(c)):
+        raise ValueError(L.epi_last_error(None).decode())
+    return c
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def counts_to_array(c):
+    return np.array([getattr(c, f) for f in COUNT_FIELDS], np.uint32)
+
+
+class EpiError(RuntimeError):
+    pass
+
+
+class Engine:
+    """One region engine resident on one GPU (`epi_engine`)."""
+
+    def __init__(self, cfg, seed=1, device=0, region=0):
+        self.L = _ffi.load()
+        self.cfg = cfg
+        h = C.c_void_p()
+        rc = self.L.epi_create_region(C.byref(cfg), seed, device, region, C.byref(h))
+        if rc:
+            raise EpiError(f"epi_create failed ({rc}): {self.L.epi_last_error(None).decode()}")
+        self.h = h
+
+    def _check(self, rc):
+        if rc:
+            raise EpiError(f"error {rc}: {self.L.epi_last_error(self.h).decode()}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.epi_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    @property
+    def population(self):
+        return self.L.epi_population(self.h)
+
+    def counts_at_start(self):
+        c = EpiCounts()
+        self._check(self.L.epi_counts_at_start(self.h, C.byref(c)))
+        return counts_to_array(c)
+
+    def set_stream(self, cuda_stream_ptr):
+        self._check(self.L.epi_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
+
+    def sync(self):
+        self._check(self.L.epi_sync(self.h))
+
+    def reset(self):
+        self._check(self.L.epi_reset(self.h))
+
+    # CitizenLocationMap::simulate for one hour
+    def step(self, hour, draws=None):
+        c = EpiCounts()
+        if draws is None:
+            self._check(self.L.epi_step(self.h, hour, C.byref(c)))
+        else:
+            draws = np.ascontiguousarray(draws, np.uint64)
+            assert draws.shape == (self.population, _ffi.EPI_DRAWS_PER_AGENT)
+            self._check(self.L.epi_step_with_draws(self.h, hour, _ptr(draws), C.byref(c)))
+        return counts_to_array(c)
+
+    def run_hours(self, first_hour, n_hours, out=None):
+        rows = out if out is not None else np.zeros((n_hours, 7), np.uint32)
+        self._check(self.L.epi_run_hours(self.h, first_hour, n_hours, _ptr(rows)))
+        return rows
+
+    def lock_city(self):
+        self._check(self.L.epi_lock_city(self.h))
+
+    def unlock_city(self):
+        self._check(self.L.epi_unlock_city(self.h))
+
+    def vaccinate(self, p, hour):
+        self._check(self.L.epi_vaccinate(self.h, p, hour))
+
+    def expand_hospital(self):
+        self._check(self.L.epi_expand_hospital(self.h))
+
+    def get_state(self):
+        n = self.population
+        arrs = {f: np.zeros(n, dt) for f, dt in zip(STATE_FIELDS, STATE_DTYPES)}
+        self._check(self.L.epi_get_state(self.h, *[_ptr(arrs[f]) for f in STATE_FIELDS]))
+        return arrs
+
+    def set_state(self, arrs):
+        a = [np.ascontiguousarray(arrs[f], dt) for f, dt in zip(STATE_FIELDS, STATE_DTYPES)]
+        self._check(self.L.epi_set_state(self.h, len(a[0]), *[_ptr(x) for x in a]))
+
+    def geometry(self):
+        out = np.zeros(19, np.int32)
+        self._check(self.L.epi_geometry(self.h, _ptr(out)))
+        return out
+
+    def get_grid(self):
+        pitch, rows = C.c_uint32(), C.c_uint32()
+        self._check(self.L.epi_get_grid(self.h, None, 0, C.byref(pitch), C.byref(rows)))
+        g = np.zeros((rows.value, pitch.value), np.uint8)
+        self._check(self.L.epi_get_grid(self.h, _ptr(g), g.size, C.byref(pitch), C.byref(rows)))
+        return g
+
+    def set_kernel_timing(self, on):
+        self._check(self.L.epi_set_kernel_timing(self.h, int(on)))
+
+    def kernel_times(self):
+        ms = np.zeros(_ffi.EPI_N_KERNEL_KINDS, np.float64)
+        n = np.zeros(_ffi.EPI_N_KERNEL_KINDS, np.uint64)
+        self._check(self.L.epi_get_kernel_times(self.h, _ptr(ms), _ptr(n)))
+        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(_ffi.KERNEL_KINDS)}
+
+    def launch_count(self, reset=False):
+        return int(self.L.epi_launch_count(self.h, int(reset)))
+
+    @property
+    def device_bytes(self):
+        return int(self.L.epi_device_bytes(self.h))
+
+
+def run_standalone(cfg, seed=1, device=0, output_dir=None, engine_id="0"):
+    """EngineApp::start_standalone: whole run with interventions; returns (rows[n,7], hour-loop seconds)."""
+    L = _ffi.load()
+    rows = np.zeros((max(int(cfg.hours), 1), 7), np.uint32)
+    n = C.c_uint32(0)
+    secs = C.c_double(0.0)
+    rc = L.epi_run_standalone(C.byref(cfg), seed, device, output_dir.encode() if output_dir else None, engine_id.encode(),
+                              _ptr(rows), rows.shape[0], C.byref(n), C.byref(secs))
+    if rc:
+        raise EpiError(f"epi_run_standalone failed ({rc}): {L.epi_last_error(None).decode()}")
+    return rows[: n.value].copy(), secs.value

@@ -1,0 +1,160 @@
+/*
+ * epi.h -- C ABI of the B200-native EpiRust per-hour agent step.
+ *
+ * This is the drop-in boundary for the reference's hot path.  The reference (thoughtworks/epirust) has no
+ * FFI: its hour loop calls Rust methods directly.  Each entry point below names the reference interface it
+ * replaces (paths relative to the reference root) so a maintainer can swap the call site for an `extern "C"`
+ * binding (see INTEGRATION.md for the Rust `extern` block).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++ / torch types.
+ *   - every call returns 0 on success, non-zero on failure; epi_last_error() gives the message.  Nothing
+ *     panics or throws across the boundary (the reference panics: allocation_map.rs:128, :222, :254 ...).
+ *   - one epi_engine == one region == one GPU + one CUDA stream.  A handle is NOT thread-safe (one caller
+ *     thread per handle, like the reference: epidemiology_simulation.rs:223-257).
+ *   - agents and the occupancy grid live in HBM for the whole run.  Only the 7 x u32 Counts row per hour
+ *     (and traveller buffers on exchange hours) cross PCIe.
+ *   - there is NO CPU fallback: every call fails with EPI_ERR_CUDA if no sm_100 device is usable.
+ */
+#ifndef EPI_H
+#define EPI_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EPI_OK 0
+#define EPI_ERR_ARG 1
+#define EPI_ERR_CUDA 2
+#define EPI_ERR_CONFIG 3
+#define EPI_ERR_IO 4
+#define EPI_ERR_STATE 5
+#define EPI_ERR_NCCL 6
+
+#define EPI_MAX_VACCINATIONS 8
+#define EPI_DRAWS_PER_AGENT 16 /* u64 draw slots per agent-hour, see DESIGN.md "Draw slots" */
+
+/* common::config::Config for Population::Auto (common/src/config/mod.rs:44-58, population.rs:36-43,
+ * common/src/disease/mod.rs:26-45, geography_parameters.rs:24-28, starting_infections.rs:22-28,
+ * intervention_config.rs:23-48).  Produced from the simulation-config JSON by epi_config_from_json(). */
+typedef struct epi_config {
+    uint32_t number_of_agents;
+    double public_transport_percentage;
+    double working_percentage;
+    uint32_t regular_transmission_start_day, high_transmission_start_day, last_day;
+    uint32_t asymptomatic_last_day, mild_infected_last_day; /* parsed, ignored like the reference (constants.rs:48-50) */
+    double regular_transmission_rate, high_transmission_rate, death_rate;
+    double percentage_asymptomatic_population, percentage_severe_infected_population;
+    uint32_t exposed_duration, pre_symptomatic_duration;
+    uint32_t grid_size;
+    double hospital_beds_percentage;
+    uint32_t hours;
+    uint32_t infected_mild_asymptomatic, infected_mild_symptomatic, infected_severe, exposed;
+    int32_t has_lockdown;
+    uint32_t lockdown_at_number_of_infections;
+    double essential_workers_population;
+    int32_t has_build_new_hospital;
+    uint32_t spread_rate_threshold;
+    int32_t n_vaccinations;
+    uint32_t vaccinate_at_hour[EPI_MAX_VACCINATIONS];
+    double vaccinate_percent[EPI_MAX_VACCINATIONS];
+} epi_config;
+
+/* engine::models::events::Counts (engine/src/models/events/counts.rs:25-34): one epicurve CSV row. */
+typedef struct epi_counts {
+    uint32_t hour, susceptible, exposed, infected, hospitalized, recovered, deceased;
+} epi_counts;
+
+typedef struct epi_engine epi_engine;
+
+/* ---- lifecycle ------------------------------------------------------------------------------------------ */
+
+/* Replaces Epidemiology::new (engine/src/epidemiology_simulation.rs:75-135): define_geography, Auto population
+ * factory, resize_hospital, CitizenLocationMap::new, init_interventions' essential-worker draw.  `seed` is the
+ * Philox key (the reference is unseeded: common/src/utils/random_wrapper.rs:23-35).  `region` is this engine's
+ * index in the travel plan (0 for standalone). */
+int epi_create(const epi_config* cfg, uint64_t seed, int device, epi_engine** out);
+int epi_create_region(const epi_config* cfg, uint64_t seed, int device, int region, epi_engine** out);
+void epi_destroy(epi_engine* e);
+/* message of the last failed call on this handle (NULL handle: last failed epi_create / global call) */
+const char* epi_last_error(const epi_engine* e);
+/* CitizenLocationMap::current_population (allocation_map.rs:389-391) */
+uint32_t epi_population(const epi_engine* e);
+/* counts_at_start (engine/src/utils/util.rs:45-51) */
+int epi_counts_at_start(const epi_engine* e, epi_counts* out);
+/* use the caller's CUDA stream (cudaStream_t as void*) for all subsequent work; NULL = the engine's own */
+int epi_set_stream(epi_engine* e, void* cuda_stream);
+int epi_sync(epi_engine* e);
+/* restore the state epi_create produced (bench: re-run from hour 1 without paying init again) */
+int epi_reset(epi_engine* e);
+
+/* ---- the hot path ----------------------------------------------------------------------------------------- */
+
+/* Replaces CitizenLocationMap::simulate (engine/src/allocation_map.rs:67-129) for one simulated hour:
+ * Citizen::perform_operation for every agent against the start-of-hour map, lowest-agent-id conflict
+ * resolution, swap, and Counts::update_counts.  out->hour = hour. */
+int epi_step(epi_engine* e, uint32_t hour, epi_counts* out);
+/* Same hour with every random draw injected: draws[agent * EPI_DRAWS_PER_AGENT + slot] (host memory).
+ * This is the bit-exact sub-step test entry (no reference equivalent; the reference cannot inject draws). */
+int epi_step_with_draws(epi_engine* e, uint32_t hour, const uint64_t* draws, epi_counts* out);
+/* n_hours consecutive epi_step calls without host synchronisation in between (CUDA-graph replay for whole
+ * days).  rows_out[n_hours].  Replaces the body of the loop at epidemiology_simulation.rs:223-246 between
+ * intervention decisions. */
+int epi_run_hours(epi_engine* e, uint32_t first_hour, uint32_t n_hours, epi_counts* rows_out);
+
+/* ---- interventions: the O(N) sweeps; the decisions stay with the host (interventions/ *.rs) ---------------- */
+/* CitizenLocationMap::lock_city (allocation_map.rs:349-356) */
+int epi_lock_city(epi_engine* e);
+/* CitizenLocationMap::unlock_city (allocation_map.rs:358-365) */
+int epi_unlock_city(epi_engine* e);
+/* CitizenLocationMap::vaccinate (allocation_map.rs:381-387); `hour` keys the draws */
+int epi_vaccinate(epi_engine* e, double vaccination_percentage, uint32_t hour);
+/* Grid::increase_hospital_size (engine/src/geography/grid.rs:233-238) */
+int epi_expand_hospital(epi_engine* e);
+
+/* ---- test harness: crafted states in, states out ------------------------------------------------------------ */
+/* Arrays of length epi_population(), in agent-id order.  st is the packed state word (DESIGN.md "Agent state
+ * word"), t0 = at_hour of Exposed / Pre, home/work = house/office index, wsa = HospitalStaff.work_start_at. */
+int epi_get_state(epi_engine* e, int32_t* cell_x, int32_t* cell_y, uint32_t* st, uint32_t* t0, uint32_t* home, uint32_t* work,
+                  uint32_t* wsa);
+int epi_set_state(epi_engine* e, uint32_t n, const int32_t* cell_x, const int32_t* cell_y, const uint32_t* st, const uint32_t* t0,
+                  const uint32_t* home, const uint32_t* work, const uint32_t* wsa);
+/* out[0..3] housing sx,sy,ex,ey; [4..7] transport; [8..11] work; [12..15] hospital (current); [16] houses; [17] offices;
+ * [18] grid_size.  (geography/mod.rs:33-70, grid.rs:240-261) */
+int epi_geometry(const epi_engine* e, int32_t* out19);
+/* raw occupancy grid bytes (pitch * rows) for invariants tests; *pitch, *rows receive the dimensions */
+int epi_get_grid(epi_engine* e, uint8_t* out, uint64_t capacity, uint32_t* pitch, uint32_t* rows);
+
+/* ---- measurement ------------------------------------------------------------------------------------------------ */
+#define EPI_N_KERNEL_KINDS 8
+/* kinds: 0 hour kernel (propose+transition+counts), 1 commit, 2 hospital scan, 3 sleep/area-reset, 4 sweeps,
+ * 5 pack, 6 unpack, 7 misc (memset etc.).  When timing is on every launch is bracketed by CUDA events on the engine's
+ * stream (this serialises nothing but adds event overhead; never on during the bench's headline timing). */
+int epi_set_kernel_timing(epi_engine* e, int on);
+int epi_get_kernel_times(epi_engine* e, double* ms_total, uint64_t* launches);
+/* number of kernel launches (graph kernel nodes included) since creation / last reset of the counter */
+uint64_t epi_launch_count(const epi_engine* e, int reset);
+/* device bytes held by the engine */
+uint64_t epi_device_bytes(const epi_engine* e);
+
+/* ---- host driver: the engine-app equivalent ----------------------------------------------------------------- */
+/* Parse the reference's simulation-config JSON (common::config::Config::read, common/src/config/mod.rs:124-128). */
+int epi_config_from_json(const char* json_path, epi_config* out);
+int epi_config_from_json_string(const char* json_text, epi_config* out);
+/* EngineApp::start_standalone (engine/src/engine_app.rs:89-106) + Epidemiology::run_single_engine
+ * (epidemiology_simulation.rs:211-274): runs the whole simulation and writes
+ * <output_dir>/output/simulation_<engine_id>_<UTC>.csv and ..._interventions.json like CsvListener
+ * (listeners/csv_service.rs:44-71) and InterventionReporter (listeners/intervention_reporter.rs:28-63).
+ * rows_out (may be NULL) receives up to max_rows rows; *n_rows the number of hours executed; *loop_seconds the
+ * hour-loop wall time (what the reference logs as Iterations/sec, epidemiology_simulation.rs:270-272). */
+int epi_run_standalone(const epi_config* cfg, uint64_t seed, int device, const char* output_dir, const char* engine_id,
+                       epi_counts* rows_out, uint32_t max_rows, uint32_t* n_rows, double* loop_seconds);
+
+const char* epi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EPI_H */
