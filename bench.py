@@ -1,0 +1,277 @@
+#!/usr/bin/env python
+"""bench.py -- agent-steps/s of the per-hour agent step on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload 10m|1m|2m|20m]
+
+A "step" is ONE SIMULATED DAY (24 simulated hours: the full daily routine of every agent of the region, i.e.
+18 active-hour passes + the sleep-hour pass) through the C ABI of include/epi.h.  `value` = agents x simulated hours
+/ second with agents and grid resident in HBM; `e2e` = the same through the C ABI from HOST buffers (population
+uploaded from host memory inside the timed region, Counts rows read back to the host every simulated day).
+One process per GPU; with N > 1 every rank runs one region of the same size (weak scaling).
+
+--impl reference times the CPU restatement of the reference algorithm (oracle/, STREAM mode: hash map, parallel phase A,
+sequential phase B) on the host cores, on a bounded sample of the same workload.  The Rust reference itself cannot be
+built in this image (no cargo/rustc), so kind = "port".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# name -> (agents, grid_size, exposed, interventions)   
+WORKLOADS = {
+    "1m": dict(n_agents=1_000_000, grid_size=2500, exposed=1000),
+    "2m": dict(n_agents=2_000_000, grid_size=3550, exposed=2000),
+    "10m": dict(n_agents=10_000_000, grid_size=7910, exposed=10_000, lockdown=(100_000, 0.1), hospital=10_000, vaccinate=((240, 0.2),)),
+    "20m": dict(n_agents=20_000_000, grid_size=11_180, exposed=20_000),
+}
+WORKLOAD_NAMES = {
+    "1m": "BASELINE config #2: single region, 1M synthetic agents, G=2500, no interventions",
+    "2m": "BASELINE config #4 region: 2M synthetic agents, G=3550",
+    "10m": "BASELINE config #3: single region, 10M synthetic agents, G=7910, lockdown + hospital build-up + vaccination",
+    "20m": "BASELINE config #5 region: 20M synthetic agents, G=11180",
+}
+ACTIVE_BYTES, SLEEP_BYTES = 82.0, 8.0  # algorithmic bytes per agent-step (rho = 0.16)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons during the timed region."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        pw = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) > 3 + k and r[3 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None, "power_w_max": max(pw) if pw else None,
+                "samples": len(sm), "reasons": reasons}
+
+
+def algorithmic_bytes(n_agents, first_hour, n_hours):
+    total = 0.0
+    for h in range(first_hour, first_hour + n_hours):
+        total += n_agents * (SLEEP_BYTES if 1 <= h % 24 <= 6 else ACTIVE_BYTES)
+    return total
+
+
+def cpu_reference(wl, steps, warmup, budget_s=150.0, threads=None):
+    """The CPU restatement of the reference algorithm on a bounded sample.  Every step = the hours 6,7,8,9 of one
+    simulated day (1 sleep + 3 active hours = the 6:18 day mix) on the full population."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_ffi as O
+
+    threads = threads or os.cpu_count() or 1
+    kw = dict(WORKLOADS[wl])
+    cfg = O.make_config(hours=1080, **kw)
+    t0 = time.time()
+    eng = O.OracleEngine(cfg, seed=1, mode="stream", threads=threads)
+    init_s = time.time() - t0
+    n = eng.population
+    per_step = []
+    done_hours = 0
+    t_begin = time.time()
+    for k in range(warmup + steps):
+        first = 24 * k + 6
+        s = eng.time_hours(first, 4)
+        if k >= warmup:
+            per_step.append(s)
+            done_hours += 4
+        if time.time() - t_begin > budget_s and len(per_step) >= 1:
+            break
+    eng.close()
+    total = sum(per_step)
+    value = n * done_hours / total
+    sample = (f"{n} agents (full population of the workload), {len(per_step)} timed steps x simulated hours 6,7,8,9 of consecutive days "
+              f"(1 sleep + 3 active = the day's 6:18 mix), oracle STREAM mode (hash map, OpenMP phase A, sequential phase B), init {init_s:.1f}s excluded")
+    return value, threads, sample, total / max(1, len(per_step)), len(per_step)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    value, threads, sample, s_per_step, done = cpu_reference(args.workload, args.steps, min(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": "agent-steps/sec", "value": value, "unit": "agent-steps/s", "n_gpus": args.gpus, "steps": done,
+        "warmup": min(args.warmup, 1), "ms_per_step": s_per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u32", "data": "synthetic",
+        "config": {"workload": WORKLOAD_NAMES[args.workload], "agents": WORKLOADS[args.workload]["n_agents"], "grid_size": WORKLOADS[args.workload]["grid_size"]},
+        "cpu_baseline": {"value": value, "unit": "agent-steps/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from epirust_b200.engine import Engine, make_config, STATE_FIELDS, STATE_DTYPES
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: epirust_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    K, W = args.steps, max(args.warmup, 3)
+    kw = dict(WORKLOADS[args.workload])
+    cfg = make_config(hours=24 * (K + W) + 1, **kw)
+    n = kw["n_agents"]
+    stream = torch.cuda.Stream()
+    eng = Engine(cfg, seed=1 + rank, device=local, region=0)
+    eng.set_stream(stream.cuda_stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    # ---------------- value: state resident in HBM ----------------
+    rows = np.zeros((24 * (K + W), 7), np.uint32)
+    with torch.cuda.stream(stream):
+        eng.simulate_hours(1, 24 * W, out=rows)  # warm-up days (also builds the day graph)
+        barrier()
+        if rank == 0:
+            sampler.start()
+        eng.launch_count(reset=True)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        got, _ = eng.simulate_hours(24 * W + 1, 24 * K, out=rows[24 * W:])
+        ev1.record(stream)
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        launches = eng.launch_count()
+        clocks = sampler.stop() if rank == 0 else None
+    assert len(got) == 24 * K
+    last_row = got[-1].tolist()
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * n * 24.0 * K / (ms_max * 1e-3)
+
+    # ---------------- per-kernel durations (CUDA events around every launch, graphs off) ----------------
+    first = 24 * (K + W) + 1
+    eng.set_kernel_timing(True)
+    eng.run_hours(first, 48)
+    kt = eng.kernel_times()
+    eng.set_kernel_timing(False)
+    hour_ms = kt["hour"][0] / max(1, kt["hour"][1])
+    commit_ms = kt["commit"][0] / max(1, kt["commit"][1])
+    sleep_ms = kt["sleep"][0] / max(1, kt["sleep"][1])
+    pass_ms = hour_ms + commit_ms
+    peak, peak_src = peaks()
+    achieved = ACTIVE_BYTES * n / (pass_ms * 1e-3) / 1e9
+    day_bytes = algorithmic_bytes(n, 24 * W + 1, 24 * K)
+    roofline = {
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "kernel": "active-hour pass = k_hour (propose + transitions + counts) + k_commit (lowest-id claim resolution)",
+        "algorithmic_bytes_per_launch": ACTIVE_BYTES * n, "avg_launch_ms": pass_ms, "peak_source": peak_src,
+        "per_kernel_ms": {"k_hour": hour_ms, "k_commit": commit_ms, "k_sleep": sleep_ms, "k_hospital_scan": kt["hospital_scan"][0] / max(1, kt["hospital_scan"][1])},
+        "whole_run_achieved_gbs": day_bytes * world / (ms_max * 1e-3) / 1e9, "whole_run_frac": day_bytes / (ms_max * 1e-3) / 1e9 / peak,
+    }
+
+    # ---------------- e2e: host buffers -> C ABI -> host rows ----------------
+    eng.reset()
+    host_state = eng.get_state()  # the initial population as host arrays (what a host-side caller owns)
+    pinned = {f: torch.from_numpy(host_state[f]).pin_memory() for f in STATE_FIELDS}
+    host_np = {f: pinned[f].numpy() for f in STATE_FIELDS}
+    h2d = sum(host_np[f].nbytes for f in STATE_FIELDS)
+    rows2 = np.zeros((24 * (K + W), 7), np.uint32)
+    barrier()
+    t0 = time.perf_counter()
+    eng.set_state(host_np)  # H2D of the whole population (cell, st, t0, home, work, wsa) + grid rebuild
+    got2, _ = eng.simulate_hours(1, 24 * K, out=rows2)  # Counts rows D2H every simulated day
+    eng.sync()
+    t1 = time.perf_counter()
+    e2e_s = torch.tensor([t1 - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = world * n * 24.0 * K / float(e2e_s.item())
+    e2e = {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": 24 * 28,
+           "note": "population uploaded from pinned host arrays once (amortised over the K days), 24 Counts rows read back per day"}
+    eng.close()
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, threads, sample, _, _ = cpu_reference(args.workload if args.workload in ("1m", "2m") else "1m", 3, 1, budget_s=25.0)
+        if args.workload not in ("1m", "2m"):
+            sample = "SUB-SAMPLE at the same density rho=0.16: " + sample
+        cpu = {"value": v, "unit": "agent-steps/s", "cores": threads, "kind": "port", "sample": sample}
+
+    if rank == 0:
+        line = {
+            "metric": "agent-steps/sec", "value": value, "unit": "agent-steps/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": {"workload": WORKLOAD_NAMES[args.workload], "agents_per_gpu": n, "grid_size": kw["grid_size"], "step": "one simulated day (24 hours)",
+                       "l2": "state + grids larger than L2 (no flush needed)" if n >= 5_000_000 else "working set fits the 126 MB L2; no flush (the real run is L2-resident too)",
+                       "regions": world, "exchange": "none (independent regions)" if world > 1 else "n/a", "last_counts_row": last_row},
+            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="10m", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -57,7 +57,7 @@ class EpiCounts(C.Structure):
 # every symbol include/epi.h declares (tests/test_abi.py checks the library exports all of them)
 EXPORTS = [
     "epi_create", "epi_create_region", "epi_destroy", "epi_last_error", "epi_population", "epi_counts_at_start", "epi_set_stream",
-    "epi_sync", "epi_reset", "epi_step", "epi_step_with_draws", "epi_run_hours", "epi_lock_city", "epi_unlock_city", "epi_vaccinate",
+    "epi_sync", "epi_reset", "epi_step", "epi_step_with_draws", "epi_run_hours", "epi_simulate_hours", "epi_intervention_events", "epi_lock_city", "epi_unlock_city", "epi_vaccinate",
     "epi_expand_hospital", "epi_get_state", "epi_set_state", "epi_geometry", "epi_get_grid", "epi_set_kernel_timing",
     "epi_get_kernel_times", "epi_launch_count", "epi_device_bytes", "epi_config_from_json", "epi_config_from_json_string",
     "epi_run_standalone", "epi_version",
@@ -92,6 +92,8 @@ def load():
     L.epi_step.argtypes = [vp, u32, C.POINTER(EpiCounts)]
     L.epi_step_with_draws.argtypes = [vp, u32, vp, C.POINTER(EpiCounts)]
     L.epi_run_hours.argtypes = [vp, u32, u32, vp]
+    L.epi_simulate_hours.argtypes = [vp, u32, u32, i32, vp, C.POINTER(u32), C.POINTER(i32)]
+    L.epi_intervention_events.argtypes = [vp, vp, u32, C.POINTER(u32)]
     L.epi_lock_city.argtypes = [vp]
     L.epi_unlock_city.argtypes = [vp]
     L.epi_vaccinate.argtypes = [vp, C.c_double, u32]

@@ -58,7 +58,7 @@ def build(force=False, verbose=False):
                     print(" ".join(cmd))
                 subprocess.check_call(cmd)
             objs.append(o)
-        cmd = [nvcc, "-shared", "-ccbin", "/usr/bin/g++", "-Xcompiler", "-fopenmp", "-o", LIB] + objs + ["-lnccl"]
+        cmd = [nvcc, "-shared", "-ccbin", "/usr/bin/g++", "-Xcompiler", "-fopenmp", "-o", LIB] + objs
         if verbose:
             print(" ".join(cmd))
         subprocess.check_call(cmd)

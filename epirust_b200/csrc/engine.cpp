@@ -286,8 +286,7 @@ int epi_create_region(const epi_config* cfg, uint64_t seed, int device, int regi
     if (prop.major != 10)
         return engine_fail(nullptr, EPI_ERR_CUDA, std::string("device ") + prop.name + " is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
                                                       "; this library is built for sm_100a only");
-    epi_engine* e = new epi_engine();
-    e->cfg = *cfg;
+    epi_engine* e = new epi_engine(*cfg);
     e->seed = seed;
     e->device = device;
     auto fail = [&](int rc) {
@@ -395,6 +394,8 @@ int epi_reset(epi_engine* e) {
     CU(cudaMemcpyAsync(e->D.wsa, e->i_wsa, nb, cudaMemcpyDeviceToDevice, e->stream));
     if (e->P.hospital_gen != 0) { e->P.hospital_gen = 0; drop_graph(e); }
     initial_counts(e);
+    e->interventions = epi::Interventions(e->cfg);
+    e->events.clear();
     return rebuild_grid(e);
 }
 

@@ -8,8 +8,10 @@
 #include "../../include/epi.h"
 #include "host_model.h"
 #include "layout.h"
+#include "simulation.h"
 
 struct epi_engine {
+    explicit epi_engine(const epi_config& c) : cfg(c), interventions(c) {}
     epi_config cfg{};
     epi::Geometry geo{};
     epi::Params P{};
@@ -40,6 +42,9 @@ struct epi_engine {
     std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> pending_events;
     uint64_t launches = 0;
     epi_counts last_counts{};
+    // host side of CitizenLocationMap::process_interventions (allocation_map.rs:306-337): the decisions
+    epi::Interventions interventions;
+    std::vector<epi_intervention_event> events;
     mutable std::string err;
 };
 

@@ -53,81 +53,99 @@ static void log_counts(const epi_counts& c) {
     std::printf("INFO - S: %u, E:%u, I: %u, H: %u, R: %u, D: %u\n", c.susceptible, c.exposed, c.infected, c.hospitalized, c.recovered, c.deceased);
 }
 
+// hours [first_hour, first_hour + n_hours): simulate + process_interventions (+ stop rule)
+static int simulate_hours(epi_engine* e, uint32_t first_hour, uint32_t n_hours, bool stop_rule, epi_counts* rows_out, uint32_t* n_rows, int* stopped,
+                          bool log, const std::chrono::steady_clock::time_point* start_time) {
+    Interventions& iv = e->interventions;
+    const uint32_t end_hour = first_hour + n_hours;  // exclusive
+    std::vector<epi_counts> seg;
+    bool stop = false;
+    uint32_t simulation_hour = first_hour, written = 0;
+    while (simulation_hour < end_hour && !stop) {
+        // Run up to (and including) the next hour at which a host decision can change device state:
+        // start of day (lockdown.rs:55, hospital.rs:55,70), a configured vaccination hour (vaccination.rs:52),
+        // the unlock hour (lockdown.rs:69-73).  The per-hour stop rule only needs the Counts rows.
+        uint32_t seg_end = (simulation_hour + 23u) / 24u * 24u;
+        seg_end = std::min(seg_end, iv.vaccinate.next_hour(simulation_hour));
+        if (iv.lockdown.is_locked_down() && iv.lockdown.unlock_hour() >= simulation_hour) seg_end = std::min(seg_end, iv.lockdown.unlock_hour());
+        seg_end = std::min(seg_end, end_hour - 1u);
+        const uint32_t n = seg_end - simulation_hour + 1u;
+        seg.resize(n);
+        int rc = epi_run_hours(e, simulation_hour, n, seg.data());
+        if (rc) return rc;
+        for (uint32_t k = 0; k < n && !stop; ++k) {
+            const epi_counts& c = seg[k];  // counts_at_hr.increment_hour() + simulate()
+            rows_out[written++] = c;       // listeners.counts_updated
+            // CitizenLocationMap::process_interventions (allocation_map.rs:306-337)
+            if (const double* pct = iv.vaccinate.get_vaccination_percentage(c)) {
+                if (log) std::printf("INFO - Vaccination\n");
+                rc = epi_vaccinate(e, *pct, c.hour);
+                if (rc) return rc;
+                e->events.push_back({c.hour, 1, 0});
+            }
+            if (iv.lockdown.should_apply(c)) {
+                iv.lockdown.apply();
+                if (log) std::printf("INFO - Locking the city. Hour: %u\n", c.hour);
+                rc = epi_lock_city(e);
+                if (rc) return rc;
+                e->events.push_back({c.hour, 0, 1});
+            }
+            if (iv.lockdown.should_unlock(c)) {
+                if (log) std::printf("INFO - Unlocking city. Hour: %u\n", c.hour);
+                rc = epi_unlock_city(e);
+                if (rc) return rc;
+                iv.lockdown.unapply();
+                e->events.push_back({c.hour, 0, 0});
+            }
+            iv.build_new_hospital.counts_updated(c);
+            if (iv.build_new_hospital.should_apply(c)) {
+                if (log) std::printf("INFO - Increasing the hospital size\n");
+                rc = epi_expand_hospital(e);
+                if (rc) return rc;
+                iv.build_new_hospital.apply();
+                e->events.push_back({c.hour, 2, 0});
+            }
+            // Epidemiology::stop_simulation, Standalone arm (epidemiology_simulation.rs:564-575)
+            if (stop_rule && c.exposed == 0 && c.infected == 0 && c.hospitalized == 0) stop = true;
+            if (!stop && c.hour % 100u == 0 && log && start_time) {
+                const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - *start_time).count();
+                std::printf("INFO - Throughput: %f iterations/sec; simulation hour %u\n", (double)c.hour / el, c.hour);
+                log_counts(c);
+            }
+        }
+        simulation_hour = seg_end + 1u;
+    }
+    *n_rows = written;
+    *stopped = stop ? 1 : 0;
+    return EPI_OK;
+}
+
 int run_single_engine(epi_engine* e, const epi_config& cfg, RunResult& result, bool log) {
-    LockdownIntervention lockdown(cfg);
-    BuildNewHospital build_new_hospital(cfg);
-    VaccinateIntervention vaccinate(cfg);
-    Listeners listeners;
     epi_counts counts_at_hr;
     int rc = epi_counts_at_start(e, &counts_at_hr);
     if (rc) return rc;
     if (log) log_counts(counts_at_hr);
     const auto start_time = std::chrono::steady_clock::now();
-    auto elapsed = [&] { return std::chrono::duration<double>(std::chrono::steady_clock::now() - start_time).count(); };
-    std::vector<epi_counts> seg;
-    bool stop = false;
-    uint32_t simulation_hour = 1;
-    while (simulation_hour < cfg.hours && !stop) {
-        // Run up to (and including) the next hour at which a host decision can change device state:
-        // start of day (lockdown.rs:55, hospital.rs:55,70), a configured vaccination hour (vaccination.rs:52),
-        // the unlock hour (lockdown.rs:69-73).  The per-hour stop rule only needs the Counts rows.
-        uint32_t seg_end = (simulation_hour + 23u) / 24u * 24u;
-        seg_end = std::min(seg_end, vaccinate.next_hour(simulation_hour));
-        if (lockdown.is_locked_down() && lockdown.unlock_hour() >= simulation_hour) seg_end = std::min(seg_end, lockdown.unlock_hour());
-        seg_end = std::min(seg_end, cfg.hours - 1u);
-        const uint32_t n = seg_end - simulation_hour + 1u;
-        seg.resize(n);
-        rc = epi_run_hours(e, simulation_hour, n, seg.data());
+    result.rows.assign(cfg.hours > 0 ? cfg.hours : 1u, epi_counts{});
+    uint32_t n_rows = 0;
+    int stopped = 0;
+    if (cfg.hours > 1) {  // for simulation_hour in 1..config.get_hours()
+        rc = simulate_hours(e, 1, cfg.hours - 1u, true, result.rows.data(), &n_rows, &stopped, log, &start_time);
         if (rc) return rc;
-        for (uint32_t k = 0; k < n && !stop; ++k) {
-            counts_at_hr = seg[k];  // counts_at_hr.increment_hour() + simulate()
-            listeners.counts_updated(counts_at_hr);
-            // CitizenLocationMap::process_interventions (allocation_map.rs:306-337)
-            if (const double* pct = vaccinate.get_vaccination_percentage(counts_at_hr)) {
-                if (log) std::printf("INFO - Vaccination\n");
-                rc = epi_vaccinate(e, *pct, counts_at_hr.hour);
-                if (rc) return rc;
-                listeners.intervention_applied(counts_at_hr.hour, vaccinate.name(), vaccinate.json_data());
-            }
-            if (lockdown.should_apply(counts_at_hr)) {
-                lockdown.apply();
-                if (log) std::printf("INFO - Locking the city. Hour: %u\n", counts_at_hr.hour);
-                rc = epi_lock_city(e);
-                if (rc) return rc;
-                listeners.intervention_applied(counts_at_hr.hour, lockdown.name(), lockdown.json_data());
-            }
-            if (lockdown.should_unlock(counts_at_hr)) {
-                if (log) std::printf("INFO - Unlocking city. Hour: %u\n", counts_at_hr.hour);
-                rc = epi_unlock_city(e);
-                if (rc) return rc;
-                lockdown.unapply();
-                listeners.intervention_applied(counts_at_hr.hour, lockdown.name(), lockdown.json_data());
-            }
-            build_new_hospital.counts_updated(counts_at_hr);
-            if (build_new_hospital.should_apply(counts_at_hr)) {
-                if (log) std::printf("INFO - Increasing the hospital size\n");
-                rc = epi_expand_hospital(e);
-                if (rc) return rc;
-                build_new_hospital.apply();
-                listeners.intervention_applied(counts_at_hr.hour, build_new_hospital.name(), build_new_hospital.json_data());
-            }
-            // Epidemiology::stop_simulation, Standalone arm (epidemiology_simulation.rs:564-575)
-            if (counts_at_hr.exposed == 0 && counts_at_hr.infected == 0 && counts_at_hr.hospitalized == 0) stop = true;
-            if (!stop && counts_at_hr.hour % 100u == 0 && log) {
-                std::printf("INFO - Throughput: %f iterations/sec; simulation hour %u of %u\n", (double)counts_at_hr.hour / elapsed(), counts_at_hr.hour, cfg.hours);
-                log_counts(counts_at_hr);
-            }
-        }
-        simulation_hour = seg_end + 1u;
     }
-    result.loop_seconds = elapsed();
-    if (log) {
-        std::printf("INFO - Number of iterations: %u, Total Time taken %f seconds\n", counts_at_hr.hour, result.loop_seconds);
-        std::printf("INFO - Iterations/sec: %f\n", (double)counts_at_hr.hour / result.loop_seconds);
-        std::printf("INFO - Agent-steps/sec: %e\n", (double)counts_at_hr.hour * (double)cfg.number_of_agents / result.loop_seconds);
+    result.rows.resize(n_rows);
+    result.loop_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - start_time).count();
+    if (log && n_rows) {
+        const uint32_t last = result.rows.back().hour;
+        std::printf("INFO - Number of iterations: %u, Total Time taken %f seconds\n", last, result.loop_seconds);
+        std::printf("INFO - Iterations/sec: %f\n", (double)last / result.loop_seconds);
+        std::printf("INFO - Agent-steps/sec: %e\n", (double)last * (double)cfg.number_of_agents / result.loop_seconds);
     }
-    result.rows = std::move(listeners.counts);
-    result.interventions = std::move(listeners.interventions);
+    static const char* names[3] = {"lockdown", "vaccination", "build_new_hospital"};
+    for (const epi_intervention_event& ev : e->events) {
+        const char* data = ev.kind == 0 ? (ev.status ? "{\"status\":\"locked_down\"}" : "{\"status\":\"lockdown_revoked\"}") : "{}";
+        result.interventions.push_back({ev.hour, names[ev.kind], data});
+    }
     return EPI_OK;
 }
 
@@ -229,6 +247,22 @@ int epi_config_from_json(const char* json_path, epi_config* out) {
         return engine_fail(nullptr, EPI_ERR_IO, ex.what());
     }
     return epi_config_from_json_string(text.c_str(), out);
+}
+
+int epi_simulate_hours(epi_engine* e, uint32_t first_hour, uint32_t n_hours, int stop_rule, epi_counts* rows_out, uint32_t* n_rows, int* stopped) {
+    if (!e || (!rows_out && n_hours) || !n_rows || !stopped) return engine_fail(e, EPI_ERR_ARG, "null argument");
+    *n_rows = 0;
+    *stopped = 0;
+    if (n_hours == 0) return EPI_OK;
+    return simulate_hours(e, first_hour, n_hours, stop_rule != 0, rows_out, n_rows, stopped, false, nullptr);
+}
+
+int epi_intervention_events(const epi_engine* e, epi_intervention_event* out, uint32_t max_events, uint32_t* n) {
+    if (!e || !n) return engine_fail(e, EPI_ERR_ARG, "null argument");
+    *n = (uint32_t)e->events.size();
+    if (out)
+        for (uint32_t i = 0; i < std::min<uint32_t>(max_events, *n); ++i) out[i] = e->events[i];
+    return EPI_OK;
 }
 
 int epi_run_standalone(const epi_config* cfg, uint64_t seed, int device, const char* output_dir, const char* engine_id, epi_counts* rows_out,

@@ -72,6 +72,14 @@ class VaccinateIntervention {
     std::map<uint32_t, double> by_hour_;
 };
 
+// engine/src/interventions/interventions.rs: the three state machines of one engine
+struct Interventions {
+    explicit Interventions(const epi_config& cfg) : vaccinate(cfg), lockdown(cfg), build_new_hospital(cfg) {}
+    VaccinateIntervention vaccinate;
+    LockdownIntervention lockdown;
+    BuildNewHospital build_new_hospital;
+};
+
 struct InterventionReport {  // listeners/intervention_reporter.rs:28-33
     uint32_t hour;
     std::string intervention, data;
@@ -81,8 +89,6 @@ struct InterventionReport {  // listeners/intervention_reporter.rs:28-33
 struct Listeners {
     std::vector<epi_counts> counts;
     std::vector<InterventionReport> interventions;
-    void counts_updated(const epi_counts& c) { counts.push_back(c); }
-    void intervention_applied(uint32_t hour, const char* name, const char* data) { interventions.push_back({hour, name, data}); }
     // writes <base>.csv and <base>_interventions.json
     void simulation_ended(const std::string& base) const;
 };

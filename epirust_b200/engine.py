@@ -147,6 +147,21 @@ class Engine:
         self._check(self.L.epi_run_hours(self.h, first_hour, n_hours, _ptr(rows)))
         return rows
 
+    # the hour-loop body of Epidemiology::run_single_engine: simulate + process_interventions (+ stop rule)
+    def simulate_hours(self, first_hour, n_hours, stop_rule=False, out=None):
+        rows = out if out is not None else np.zeros((n_hours, 7), np.uint32)
+        n, stopped = C.c_uint32(0), C.c_int(0)
+        self._check(self.L.epi_simulate_hours(self.h, first_hour, n_hours, int(stop_rule), _ptr(rows), C.byref(n), C.byref(stopped)))
+        return rows[: n.value], bool(stopped.value)
+
+    def intervention_events(self):
+        n = C.c_uint32(0)
+        self._check(self.L.epi_intervention_events(self.h, None, 0, C.byref(n)))
+        ev = np.zeros((n.value, 3), np.int32)
+        if n.value:
+            self._check(self.L.epi_intervention_events(self.h, _ptr(ev), n.value, C.byref(n)))
+        return ev
+
     def lock_city(self):
         self._check(self.L.epi_lock_city(self.h))
 

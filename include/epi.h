@@ -67,6 +67,15 @@ typedef struct epi_counts {
     uint32_t hour, susceptible, exposed, infected, hospitalized, recovered, deceased;
 } epi_counts;
 
+/* one InterventionReport (engine/src/listeners/intervention_reporter.rs:28-33).  kind: 0 lockdown, 1 vaccination,
+ * 2 build_new_hospital (InterventionType::name, lockdown.rs:104-114, vaccination.rs:58-64, hospital.rs:78-84);
+ * status: lockdown 1 = "locked_down", 0 = "lockdown_revoked"; otherwise 0 (json_data is {}). */
+typedef struct epi_intervention_event {
+    uint32_t hour;
+    int32_t kind;
+    int32_t status;
+} epi_intervention_event;
+
 typedef struct epi_engine epi_engine;
 
 /* ---- lifecycle ------------------------------------------------------------------------------------------ */
@@ -103,6 +112,18 @@ int epi_step_with_draws(epi_engine* e, uint32_t hour, const uint64_t* draws, epi
  * days).  rows_out[n_hours].  Replaces the body of the loop at epidemiology_simulation.rs:223-246 between
  * intervention decisions. */
 int epi_run_hours(epi_engine* e, uint32_t first_hour, uint32_t n_hours, epi_counts* rows_out);
+
+/* The body of the hour loop of Epidemiology::run_single_engine (epidemiology_simulation.rs:223-257) for hours
+ * first_hour .. first_hour+n_hours-1: counts.increment_hour, simulate, listeners.counts_updated,
+ * process_interventions (allocation_map.rs:306-337: vaccinate / lock / unlock / build hospital, decided on the host from
+ * the Counts row exactly like interventions/ *.rs, applied by the sweep kernels), and, when `stop_rule` is non-zero,
+ * Epidemiology::stop_simulation's Standalone arm (:564-575).  The device runs ahead to the next hour at which a host
+ * decision can change device state (start of day, a configured vaccination hour, the unlock hour), so Counts cross PCIe
+ * once per simulated day.  *n_rows = rows written (< n_hours only if the stop rule fired; *stopped = 1 then). */
+int epi_simulate_hours(epi_engine* e, uint32_t first_hour, uint32_t n_hours, int stop_rule, epi_counts* rows_out, uint32_t* n_rows,
+                       int* stopped);
+/* InterventionReporter's list since epi_create / epi_reset; out may be NULL to query *n only */
+int epi_intervention_events(const epi_engine* e, epi_intervention_event* out, uint32_t max_events, uint32_t* n);
 
 /* ---- interventions: the O(N) sweeps; the decisions stay with the host (interventions/ *.rs) ---------------- */
 /* CitizenLocationMap::lock_city (allocation_map.rs:349-356) */
