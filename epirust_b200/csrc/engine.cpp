@@ -78,9 +78,11 @@ void drain_events(epi_engine* e) {
 }
 
 size_t n_cells(const epi_engine* e) { return (size_t)e->geo.pitch * e->geo.rows; }
+// grid allocation: GRID_YPAD zero rows above and below, GRID_XPAD zero bytes before row 0 (5x5 window loads need no bounds checks)
+size_t grid_alloc_bytes(const epi_engine* e) { return (size_t)e->geo.pitch * (e->geo.rows + 2 * GRID_YPAD) + 2 * GRID_XPAD; }
 
 int rebuild_grid(epi_engine* e) {
-    CU(cudaMemsetAsync(e->D.grid, 0, n_cells(e), e->stream));
+    CU(cudaMemsetAsync(e->grid_alloc, 0, grid_alloc_bytes(e), e->stream));
     CU(cudaMemsetAsync(e->d_misc, 0, 2 * sizeof(uint32_t), e->stream));
     {
         Timed t(e, KK_MISC);
@@ -118,7 +120,7 @@ int enqueue_hour(epi_engine* e, uint32_t hour, uint32_t hour_offset, bool inject
     }
     {
         Timed t(e, KK_HOUR);
-        launch_hour(e->P, e->D, hour_offset, inject, e->stream);
+        launch_hour(e->P, e->D, h, hour_offset, inject, e->stream);
     }
     {
         Timed t(e, KK_COMMIT);
@@ -311,7 +313,8 @@ int epi_create_region(const epi_config* cfg, uint64_t seed, int device, int regi
         ok &= dev_alloc(e, &e->D.work, n) == cudaSuccess;
         ok &= dev_alloc(e, &e->D.wsa, n) == cudaSuccess;
         ok &= dev_alloc(e, &e->D.prop, n) == cudaSuccess;
-        ok &= dev_alloc(e, &e->D.grid, cells + 4) == cudaSuccess;
+        ok &= dev_alloc(e, &e->grid_alloc, grid_alloc_bytes(e)) == cudaSuccess;
+        e->D.grid = e->grid_alloc ? e->grid_alloc + (size_t)e->geo.pitch * GRID_YPAD + GRID_XPAD : nullptr;
         ok &= dev_alloc(e, &e->D.claim, cells) == cudaSuccess;
         ok &= dev_alloc(e, &e->D.counts, (size_t)RING_ROWS * 8) == cudaSuccess;
         ok &= dev_alloc(e, &e->d_clock, 1) == cudaSuccess;
@@ -348,7 +351,7 @@ void epi_destroy(epi_engine* e) {
     if (e->stream) cudaStreamSynchronize(e->stream);
     drop_graph(e);
     for (auto& pe : e->pending_events) { cudaEventDestroy(pe.second.first); cudaEventDestroy(pe.second.second); }
-    void* ptrs[] = {e->D.cell, e->D.st, e->D.t0, e->D.home, e->D.work, e->D.wsa, e->D.prop, e->D.grid, e->D.claim, e->D.counts,
+    void* ptrs[] = {e->D.cell, e->D.st, e->D.t0, e->D.home, e->D.work, e->D.wsa, e->D.prop, e->grid_alloc, e->D.claim, e->D.counts,
                     e->d_clock, e->d_misc, e->d_draws, e->i_cell, e->i_st, e->i_t0, e->i_home, e->i_work, e->i_wsa};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (e->h_counts) cudaFreeHost(e->h_counts);
@@ -483,8 +486,8 @@ int epi_get_state(epi_engine* e, int32_t* cx, int32_t* cy, uint32_t* st, uint32_
         // canonical form: fields that the reference's enum variant does not carry read as 0
         const uint32_t state = st[i] & ST_STATE_MASK, sev = (st[i] >> ST_SEV_SHIFT) & 3u, ws = (st[i] >> ST_WS_SHIFT) & 3u;
         if (!(state == ST_E || (state == ST_I && sev == SEV_PRE))) t0[i] = 0;
-        home[i] &= INDEX_MASK;
-        work[i] = ws == WS_NA ? 0u : (work[i] & INDEX_MASK);
+        home[i] = house_index_of(e->geo, home[i]);
+        work[i] = ws == WS_NA ? 0u : office_index_of(e->geo, work[i]);
         if (ws != WS_STAFF) wsa[i] = 0;
     }
     return EPI_OK;
@@ -505,8 +508,8 @@ int epi_set_state(epi_engine* e, uint32_t n, const int32_t* cx, const int32_t* c
             return engine_fail(e, EPI_ERR_ARG, "epi_set_state: house/office index out of range");
         a.cell[i] = ((uint32_t)cy[i] << CELL_BITS) | (uint32_t)cx[i];
         a.st[i] = st[i]; a.t0[i] = t0[i];
-        a.home[i] = home[i] | ((uint32_t)e->P.region << REGION_SHIFT);
-        a.work[i] = work[i] | ((uint32_t)e->P.region << REGION_SHIFT);
+        a.home[i] = house_origin(e->geo, home[i]);
+        a.work[i] = ws == WS_NA ? 0u : office_origin(e->geo, work[i]);
         a.wsa[i] = wsa[i];
     }
     int rc = upload_agents(e, a);

@@ -52,8 +52,8 @@ Geometry make_geometry(uint32_t grid_size, uint32_t n_agents, double beds_pct) {
     // Grid::increase_hospital_size (grid.rs:233-238)
     g.hospital_expanded = Rect{g.hospital_initial.sx, g.hospital_initial.sy, G, G};
     const int max_x = std::max(std::max(g.hospital_initial.ex, g.hospital_expanded.ex), G);
-    g.pitch = (uint32_t)max_x + 1u;
-    g.pitch = (g.pitch + 3u) & ~3u;  // rows start on 4-byte boundaries (word-wise grid build)
+    g.pitch = (uint32_t)max_x + 2u;      // one always-vacant padding column right of the last cell
+    g.pitch = (g.pitch + 15u) & ~15u;  // rows start on 16-byte boundaries
     g.rows = (uint32_t)G + 1u;
     return g;
 }
@@ -142,8 +142,8 @@ void build_population(const epi_config& c, const Geometry& g, uint64_t seed, int
         const uint32_t immunity_plus2 = (uint32_t)mulhi64(draw(i, IS_IMMUNITY), 5);
         out.st[i] = ST_S | (immunity_plus2 << ST_IMM_SHIFT) | (pt ? ST_PT : 0u) | (ws << ST_WS_SHIFT) | (AK_HOME << ST_AREA_SHIFT);
         out.t0[i] = 0;
-        out.home[i] = (i % g.n_houses) | ((uint32_t)region << REGION_SHIFT);
-        out.work[i] = working ? ((i % g.n_offices) | ((uint32_t)region << REGION_SHIFT)) : 0u;
+        out.home[i] = house_origin(g, i % g.n_houses);
+        out.work[i] = working ? office_origin(g, i % g.n_offices) : 0u;
         out.wsa[i] = ws == WS_STAFF ? kRoutineWorkTime : 0u;
     }
 

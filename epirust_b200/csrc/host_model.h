@@ -22,6 +22,22 @@ struct Geometry {
 // geography::define_geography + Grid::resize_hospital (geography/mod.rs:33-70, grid.rs:240-261)
 Geometry make_geometry(uint32_t grid_size, uint32_t n_agents, double hospital_beds_percentage);
 
+// house / office index (row-major in area_factory order, geography/area.rs:95-117) <-> packed origin cell
+inline uint32_t house_origin(const Geometry& g, uint32_t idx) {
+    return ((uint32_t)(g.housing.sy + 2 * (int)(idx / (uint32_t)g.house_nx)) << CELL_BITS) | (uint32_t)(g.housing.sx + 2 * (int)(idx % (uint32_t)g.house_nx));
+}
+inline uint32_t office_origin(const Geometry& g, uint32_t idx) {
+    return ((uint32_t)(g.work.sy + 10 * (int)(idx / (uint32_t)g.office_nx)) << CELL_BITS) | (uint32_t)(g.work.sx + 10 * (int)(idx % (uint32_t)g.office_nx));
+}
+inline uint32_t house_index_of(const Geometry& g, uint32_t origin) {
+    const int x = (int)(origin & CELL_XMASK), y = (int)((origin >> CELL_BITS) & CELL_XMASK);
+    return (uint32_t)((y - g.housing.sy) / 2 * g.house_nx + (x - g.housing.sx) / 2);
+}
+inline uint32_t office_index_of(const Geometry& g, uint32_t origin) {
+    const int x = (int)(origin & CELL_XMASK), y = (int)((origin >> CELL_BITS) & CELL_XMASK);
+    return (uint32_t)((y - g.work.sy) / 10 * g.office_nx + (x - g.work.sx) / 10);
+}
+
 struct HostAgents {
     std::vector<uint32_t> cell, st, t0, home, work, wsa;
     size_t size() const { return st.size(); }

@@ -1,9 +1,10 @@
 // sm_100a kernels of the per-hour agent step.  HBM/L2-bound integer work: no tensor cores.
 //
 //   k_hospital_scan   first vacant hospital cell in row-major order        (allocation_map.rs:144-147)
-//   k_hour<INJECT>    one agent per thread: routine, movement proposal against the start-of-hour grid, disease
+//   k_hour<KIND>      one agent per thread: routine, movement proposal against the start-of-hour grid, disease
 //                     transition, Counts; atomicMax claim on the target cell (citizen/mod.rs:227-432,
-//                     default_disease_handler.rs:31-103, counts.rs:126-140)
+//                     default_disease_handler.rs:31-103, counts.rs:126-140).  KIND: the hour-of-day class
+//                     (0 = ROUTINE_START_TIME, 23 = ROUTINE_END_TIME, else perform_movements) -- uniform per launch.
 //   k_commit          lowest-id claimant moves, loser stays; grid bytes updated in place (allocation_map.rs:93-102,131-134)
 //   k_sleep           hours 1..6: current_area := home (citizen/mod.rs:244-248) + Counts
 //   k_lock / k_unlock / k_vaccinate   intervention sweeps (allocation_map.rs:349-387)
@@ -13,6 +14,11 @@
 // CitizenLocationMap::move_agent or an is_cell_vacant filter), every cell that is cleared was occupied at the start
 // of the hour, so the set of written-to-occupied and written-to-vacant cells are disjoint, and all reads of the grid
 // happen in k_hour, all writes in k_commit.
+//
+// Instruction budget: the kernel is issue-bound before it is HBM-bound, so the agent-hour is written branch-light:
+// the movement rule of the hour is reduced to (mode, rectangle) by predicated integer logic, one Philox block serves
+// the common case, the 3x3 neighbourhood is loaded unconditionally from the zero-padded grid and reduced with
+// byte-SIMD intrinsics.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -22,23 +28,17 @@
 
 namespace epi {
 
-// Moore neighbourhood in the reference's iterator order (geography/point.rs:59)
-__constant__ int c_dx[8] = {-1, 0, 1, -1, 1, -1, 0, 1};
-__constant__ int c_dy[8] = {-1, -1, -1, 0, 0, 1, 1, 1};
+enum : int { MODE_STAY = 0, MODE_WALK = 1, MODE_GOTO = 2 };
+enum : int { KIND_START = 0, KIND_MOVE = 1, KIND_END = 2 };
 
 __device__ __forceinline__ bool rect_contains(const Rect& r, int x, int y) { return r.sx <= x && r.ex >= x && r.sy <= y && r.ey >= y; }
-__device__ __forceinline__ bool rect_eq(const Rect& a, const Rect& b) { return a.sx == b.sx && a.sy == b.sy && a.ex == b.ex && a.ey == b.ey; }
 
-__device__ __forceinline__ Rect house_rect(const Params& P, uint32_t idx) {
-    const int hx = (int)(idx % (uint32_t)P.house_nx), hy = (int)(idx / (uint32_t)P.house_nx);
+__device__ __forceinline__ Rect origin_rect(uint32_t packed, int size_minus_1) {
     Rect r;
-    r.sx = P.housing.sx + 2 * hx; r.sy = P.housing.sy + 2 * hy; r.ex = r.sx + 1; r.ey = r.sy + 1;
-    return r;
-}
-__device__ __forceinline__ Rect office_rect(const Params& P, uint32_t idx) {
-    const int ox = (int)(idx % (uint32_t)P.office_nx), oy = (int)(idx / (uint32_t)P.office_nx);
-    Rect r;
-    r.sx = P.work.sx + 10 * ox; r.sy = P.work.sy + 10 * oy; r.ex = r.sx + 9; r.ey = r.sy + 9;
+    r.sx = (int)(packed & CELL_XMASK);
+    r.sy = (int)((packed >> CELL_BITS) & CELL_XMASK);
+    r.ex = r.sx + size_minus_1;
+    r.ey = r.sy + size_minus_1;
     return r;
 }
 
@@ -57,63 +57,105 @@ __device__ __forceinline__ uint32_t cell_byte(const Params& P, uint32_t s) {
     return 1u;
 }
 
+// The 8 Moore neighbours of (cx, cy) in the reference's iterator order (geography/point.rs:59):
+// j: 0 (-1,-1) 1 (0,-1) 2 (1,-1) 3 (-1,0) 4 (1,0) 5 (-1,1) 6 (0,1) 7 (1,1)
+struct Hood {
+    uint32_t lo, hi;  // grid bytes of neighbours 0..3 and 4..7
+};
+// 5x5 window of grid bytes centred on (cx, cy): row r (dy = r - 2) holds cells cx-2..cx+2 in bytes 0..4 of w[r].
+// Loaded as 10 independent aligned 32-bit loads so that one memory round trip serves both the walk (3x3 around the
+// base cell) and the exposure scan (3x3 around the proposed cell, at most one step away).  The grid allocation is
+// zero-padded by GRID_YPAD rows and GRID_XPAD bytes, so no bounds checks are needed.
+struct Window {
+    uint64_t w[5];
+};
+__device__ __forceinline__ Window load_window(const uint8_t* __restrict__ grid, uint32_t pitch, int cx, int cy) {
+    const ptrdiff_t first = (ptrdiff_t)(cy - 2) * (ptrdiff_t)pitch + (cx - 2);  // offset of the window's top-left cell
+    const ptrdiff_t aligned = first & ~(ptrdiff_t)3;                            // grid base and pitch are multiples of 4
+    const uint32_t sh = (uint32_t)(first & 3) * 8u;
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(grid + aligned);
+    const uint32_t stride = pitch >> 2;
+    uint32_t a[5], b[5];
+#pragma unroll
+    for (int r = 0; r < 5; ++r) {
+        a[r] = __ldg(p + (size_t)r * stride);
+        b[r] = __ldg(p + (size_t)r * stride + 1);
+    }
+    Window win;
+#pragma unroll
+    for (int r = 0; r < 5; ++r) win.w[r] = (((uint64_t)b[r] << 32) | a[r]) >> sh;
+    return win;
+}
+// the 3x3 neighbourhood of the cell at offset (dx, dy) from the window centre, dx, dy in {-1, 0, 1}
+__device__ __forceinline__ Hood hood_at(const Window& win, int dx, int dy) {
+    const uint64_t r0 = dy < 0 ? win.w[0] : dy == 0 ? win.w[1] : win.w[2];
+    const uint64_t r1 = dy < 0 ? win.w[1] : dy == 0 ? win.w[2] : win.w[3];
+    const uint64_t r2 = dy < 0 ? win.w[2] : dy == 0 ? win.w[3] : win.w[4];
+    const uint32_t sh = (uint32_t)(dx + 1) * 8u;
+    const uint32_t top = (uint32_t)(r0 >> sh), mid = (uint32_t)(r1 >> sh), bot = (uint32_t)(r2 >> sh);
+    Hood h;
+    h.lo = (top & 0x00FFFFFFu) | (mid << 24);
+    h.hi = ((mid >> 16) & 0xFFu) | (bot << 8);
+    return h;
+}
+// per-byte predicate words (0xFF / 0x00 per byte) -> 8-bit neighbour mask
+__device__ __forceinline__ uint32_t mask_of(uint32_t lo_pred, uint32_t hi_pred) {
+    const uint32_t a = ((lo_pred & 0x08040201u) * 0x01010101u) >> 24;
+    const uint32_t b = ((hi_pred & 0x08040201u) * 0x01010101u) >> 24;
+    return a | (b << 4);
+}
+// Area::get_neighbors_of(c).filter(is_point_in_grid): which neighbours of (cx, cy) lie inside rectangle r and the grid
+// (geography/area.rs:56-58, allocation_map.rs:156-159).  (cx, cy) itself need not be inside r.
+__device__ __forceinline__ uint32_t valid_mask(const Rect& r, int G, int cx, int cy) {
+    const int ex = min(r.ex, G - 1), ey = min(r.ey, G - 1);  // r.sx, r.sy >= 0 always
+    const uint32_t cl = (cx - 1 >= r.sx) & (cx - 1 <= ex), cc = (cx >= r.sx) & (cx <= ex), cr = (cx + 1 >= r.sx) & (cx + 1 <= ex);
+    const uint32_t ru = (cy - 1 >= r.sy) & (cy - 1 <= ey), rc = (cy >= r.sy) & (cy <= ey), rd = (cy + 1 >= r.sy) & (cy + 1 <= ey);
+    const uint32_t cols = cl | (cc << 1) | (cr << 2);
+    return (cols & (0u - ru)) | (((cl | (cr << 1)) & (0u - rc)) << 3) | ((cols & (0u - rd)) << 5);
+}
+// position of the idx-th set bit of an 8-bit mask (idx < popc(m))
+__device__ __forceinline__ int select_bit(uint32_t m, uint32_t idx) {
+    int base = 0;
+    uint32_t c = __popc(m & 0xFu);
+    if (idx >= c) { idx -= c; m >>= 4; base = 4; }
+    c = __popc(m & 0x3u);
+    if (idx >= c) { idx -= c; m >>= 2; base += 2; }
+    c = m & 1u;
+    if (idx >= c) base += 1;
+    return base;
+}
+__device__ __forceinline__ int hood_dx(int j) { return (int)((0x9224u >> (2 * j)) & 3u) - 1; }  // {-1,0,1,-1,1,-1,0,1}
+__device__ __forceinline__ int hood_dy(int j) { return (int)((0xA940u >> (2 * j)) & 3u) - 1; }  // {-1,-1,-1,0,0,1,1,1}
+
 template <bool INJECT>
 struct Draws {
     uint64_t seed;
     uint32_t agent, hour;
     const uint64_t* row;
-    __device__ __forceinline__ uint64_t get(uint32_t slot) const {
-        if (INJECT) return row[slot];
-        return philox_draw(seed, agent, hour, DOM_STEP, slot);
+    __device__ __forceinline__ U4 block(uint32_t b) const { return philox4x32_10(agent, hour, b, DOM_STEP, (uint32_t)seed, (uint32_t)(seed >> 32)); }
+    // block 0: PICK, FACTOR, A
+    __device__ __forceinline__ void common(uint32_t& pick, uint32_t& factor, uint64_t& a) const {
+        if (INJECT) { pick = (uint32_t)row[SLOT_PICK]; factor = (uint32_t)row[SLOT_FACTOR]; a = row[SLOT_A]; return; }
+        const U4 o = block(0);
+        pick = o.x; factor = o.y; a = u64_of(o.z, o.w);
     }
-    // slots 2k and 2k+1 with one Philox call
-    __device__ __forceinline__ void pair(uint32_t even_slot, uint64_t& a, uint64_t& b) const {
-        if (INJECT) { a = row[even_slot]; b = row[even_slot + 1]; return; }
-        const U4 o = philox4x32_10(agent, hour, even_slot >> 1, DOM_STEP, (uint32_t)seed, (uint32_t)(seed >> 32));
-        a = (uint64_t)o.x | ((uint64_t)o.y << 32);
-        b = (uint64_t)o.z | ((uint64_t)o.w << 32);
+    // block 1: Area::get_random_point (geography/area.rs:76-81)
+    __device__ __forceinline__ void point(const Rect& r, int& px, int& py) const {
+        uint32_t dx, dy;
+        if (INJECT) { dx = (uint32_t)row[SLOT_PX]; dy = (uint32_t)row[SLOT_PY]; }
+        else { const U4 o = block(1); dx = o.x; dy = o.y; }
+        px = r.sx + (int)mulhi32(dx, (uint32_t)(r.ex - r.sx + 1));
+        py = r.sy + (int)mulhi32(dy, (uint32_t)(r.ey - r.sy + 1));
+    }
+    __device__ __forceinline__ uint64_t expose(int j) const {
+        if (INJECT) return row[SLOT_EXPOSE0 + j];
+        const U4 o = block(2u + ((uint32_t)j >> 1));
+        return (j & 1) ? u64_of(o.z, o.w) : u64_of(o.x, o.y);
     }
 };
-enum : uint32_t { SLOT_PX = 0, SLOT_PY = 1, SLOT_PICK = 2, SLOT_A = 3, SLOT_B = 4, SLOT_EXPOSE0 = 8 };
-
-struct Mover {
-    const Params& P;
-    const uint8_t* __restrict__ grid;
-    __device__ __forceinline__ bool vacant(int x, int y) const { return grid[(size_t)y * P.pitch + (size_t)x] == 0; }
-    __device__ __forceinline__ bool in_grid(int x, int y) const { return x >= 0 && y >= 0 && x < P.grid_size && y < P.grid_size; }
-};
-
-// Area::get_random_point (geography/area.rs:76-81)
-template <bool INJECT>
-__device__ __forceinline__ void random_point(const Draws<INJECT>& dr, const Rect& r, int& px, int& py) {
-    uint64_t a, b;
-    dr.pair(SLOT_PX, a, b);
-    px = r.sx + (int)mulhi64(a, (uint64_t)(r.ex - r.sx + 1));
-    py = r.sy + (int)mulhi64(b, (uint64_t)(r.ey - r.sy + 1));
-}
-
-// Citizen::move_agent_from (citizen/mod.rs:415-432).  pick_draw: slot SLOT_PICK
-template <bool INJECT>
-__device__ __forceinline__ void walk(const Mover& mv, const Draws<INJECT>& dr, const Rect& area, bool can_move, int x, int y, int& tx, int& ty) {
-    tx = x; ty = y;
-    if (!can_move) return;
-    int lx = x, ly = y;
-    if (!rect_contains(area, x, y)) random_point(dr, area, lx, ly);
-    uint32_t mask = 0;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int nx = lx + c_dx[j], ny = ly + c_dy[j];
-        if (rect_contains(area, nx, ny) && mv.in_grid(nx, ny) && mv.vacant(nx, ny)) mask |= 1u << j;
-    }
-    const int k = __popc(mask);
-    if (k == 0) return;
-    const uint32_t idx = (uint32_t)mulhi64(dr.get(SLOT_PICK), (uint64_t)k);
-    const int j = (int)__fns(mask, 0, (int)idx + 1);
-    tx = lx + c_dx[j]; ty = ly + c_dy[j];
-}
 
 __device__ __forceinline__ void block_count(uint32_t cat, uint32_t* __restrict__ out_row) {
-    // warp-shuffle/ballot reduction -> shared -> one atomic per category per block (counts.rs:126-140)
+    // warp ballots -> shared -> one atomic per category per block (counts.rs:126-140)
     __shared__ uint32_t s_cnt[6];
     if (threadIdx.x < 6) s_cnt[threadIdx.x] = 0;
     __syncthreads();
@@ -121,7 +163,7 @@ __device__ __forceinline__ void block_count(uint32_t cat, uint32_t* __restrict__
 #pragma unroll
     for (uint32_t c = 0; c < 6; ++c) {
         const unsigned b = __ballot_sync(0xFFFFFFFFu, cat == c);
-        if (lane == 0 && b) atomicAdd(&s_cnt[c], (uint32_t)__popc(b));
+        if (lane == c && b) atomicAdd(&s_cnt[c], (uint32_t)__popc(b));
     }
     __syncthreads();
     if (threadIdx.x < 6 && s_cnt[threadIdx.x]) atomicAdd(&out_row[threadIdx.x], s_cnt[threadIdx.x]);
@@ -142,59 +184,67 @@ __global__ void __launch_bounds__(256) k_hospital_scan(Params P, const uint8_t* 
     }
 }
 
-template <bool INJECT>
+template <int KIND, bool INJECT>
 __global__ void __launch_bounds__(256) k_hour(Params P, DevPtrs D, uint32_t hour_offset) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t hour = D.clock->hour_base + hour_offset;
-    const uint32_t h = hour % 24u;
     uint32_t cat = 6;
     if (i < P.n) {
         const uint32_t s0 = D.st[i];
         const uint32_t c0 = D.cell[i];
+        const uint32_t hm = D.home[i];
+        const uint32_t wk = KIND == KIND_MOVE ? D.work[i] : 0u;  // all four loads issued together: one memory round trip
         const int x = (int)(c0 & CELL_XMASK), y = (int)(c0 >> CELL_BITS);
+        const uint8_t* __restrict__ grid = D.grid;
         uint32_t s = s0;
         int tx = x, ty = y;
-        const Mover mv{P, D.grid};
-        Draws<INJECT> dr{P.seed, i, hour, INJECT ? D.draws + (size_t)i * 16 : nullptr};
-        const uint32_t ws = (s >> ST_WS_SHIFT) & 3u;
-        uint32_t state = s & ST_STATE_MASK, sev = (s >> ST_SEV_SHIFT) & 3u, day = s >> ST_DAY_SHIFT;
-        const int imm = (int)((s >> ST_IMM_SHIFT) & 7u) - 2;
-        const Rect home = house_rect(P, D.home[i] & INDEX_MASK);
+        const Draws<INJECT> dr{P.seed, i, hour, INJECT ? D.draws + (size_t)i * 16 : nullptr};
+        const uint32_t ws = (s0 >> ST_WS_SHIFT) & 3u;
+        uint32_t state = s0 & ST_STATE_MASK, sev = (s0 >> ST_SEV_SHIFT) & 3u, day = s0 >> ST_DAY_SHIFT;
+        const Rect home = origin_rect(hm, 1);
 
-        if (h == 0) {
+        if (KIND == KIND_START) {
             // ROUTINE_START_TIME: increment_infection_day + hospitalize (citizen/mod.rs:240-243, :351-365)
-            if (state == ST_I) day = min(day + 1u, ST_DAY_MAX);
-            if (!(s & ST_HOSP) && state == ST_I && sev == SEV_SEVERE && ((P.hospitalize_mask >> rate_class(P, (uint32_t)((int)day + imm))) & 1u)) {
-                const uint32_t first = *D.hosp_first;
-                if (first != HOSP_NONE) {  // goto_hospital: every admitted agent targets the same first vacant cell
-                    const Rect hr = P.hospital[P.hospital_gen];
-                    const uint32_t w = (uint32_t)(hr.ex - hr.sx + 1);
-                    tx = hr.sx + (int)(first % w); ty = hr.sy + (int)(first / w);
-                    s |= ST_HOSP;
-                } else {  // hospital full: try a random point of the own house
-                    int px, py;
-                    random_point(dr, home, px, py);
-                    if (mv.vacant(px, py)) { tx = px; ty = py; }
+            if (state == ST_I) {
+                day = min(day + 1u, ST_DAY_MAX);
+                const int imm = (int)((s0 >> ST_IMM_SHIFT) & 7u) - 2;
+                if (!(s0 & ST_HOSP) && sev == SEV_SEVERE && ((P.hospitalize_mask >> rate_class(P, (uint32_t)((int)day + imm))) & 1u)) {
+                    const uint32_t first = *D.hosp_first;
+                    if (first != HOSP_NONE) {  // goto_hospital: every admitted agent targets the same first vacant cell
+                        const Rect hr = P.hospital[P.hospital_gen];
+                        const uint32_t w = (uint32_t)(hr.ex - hr.sx + 1);
+                        tx = hr.sx + (int)(first % w); ty = hr.sy + (int)(first / w);
+                        s |= ST_HOSP;
+                    } else {  // hospital full: try a random point of the own house
+                        int px, py;
+                        dr.point(home, px, py);
+                        if (grid[(size_t)py * P.pitch + px] == 0) { tx = px; ty = py; }
+                    }
                 }
             }
-        } else if (h == 23) {
+        } else if (KIND == KIND_END) {
             // ROUTINE_END_TIME: Citizen::deceased + on_routine_end (citizen/mod.rs:397-413, default_disease_handler.rs:88-103)
             if (state == ST_I) {
                 if ((sev == SEV_ASYM && day == 9u) || (sev == SEV_MILD && day == 12u)) state = ST_R;
-                else if (sev == SEV_SEVERE && day == P.last_day) state = bernoulli(dr.get(SLOT_A), P.thr_death) ? ST_D : ST_R;
+                else if (sev == SEV_SEVERE && day == P.last_day) {
+                    uint32_t pick, factor; uint64_t a;
+                    dr.common(pick, factor, a);
+                    state = bernoulli(a, P.thr_death) ? ST_D : ST_R;
+                }
             }
             if (state == ST_R) {  // every recovered agent, every day
                 int px, py;
-                random_point(dr, home, px, py);
-                if (mv.vacant(px, py)) { tx = px; ty = py; }
+                dr.point(home, px, py);
+                if (grid[(size_t)py * P.pitch + px] == 0) { tx = px; ty = py; }
             }
             if (state == ST_R || state == ST_D) { s &= ~ST_HOSP; sev = 0; day = 0; }
         } else {
             // perform_movements (citizen/mod.rs:257-349); h in 7..22 here (sleep hours use k_sleep)
-            const uint32_t kind0 = (s >> ST_AREA_SHIFT) & 7u;
-            const bool symptomatic = state == ST_I && (sev == SEV_MILD || sev == SEV_SEVERE);
-            const bool can_move = !(symptomatic || (s & ST_HOSP) || state == ST_D || (s & ST_ISO));  // citizen/mod.rs:452-454
-            const Rect workr = ws == WS_NA ? home : office_rect(P, D.work[i] & INDEX_MASK);
+            const uint32_t h = hour % 24u;
+            const uint32_t kind0 = (s0 >> ST_AREA_SHIFT) & 7u;
+            const bool symptomatic = state == ST_I && sev >= SEV_MILD;
+            const bool can_move = !(symptomatic || (s0 & (ST_HOSP | ST_ISO)) || state == ST_D);  // citizen/mod.rs:452-454
+            const Rect workr = ws == WS_NA ? home : origin_rect(wk, 9);
             auto rect_of = [&](uint32_t kind) -> Rect {
                 switch (kind) {
                     case AK_HOME: return home;
@@ -205,64 +255,88 @@ __global__ void __launch_bounds__(256) k_hour(Params P, DevPtrs D, uint32_t hour
                     default: return P.hospital[1];
                 }
             };
-            const Rect cur0 = rect_of(kind0);
+            // the hour's rule -> (mode, rectangle R, new current_area kind).  goto_area for a non-working agent is
+            // move_agent_from in the (old) current_area (citizen/mod.rs:386-394), i.e. MODE_WALK.
+            Rect R = rect_of(kind0);
             uint32_t kind = kind0;
-            bool dynamics = true;
-            // Citizen::goto_area (citizen/mod.rs:367-395)
-            auto goto_area = [&](const Rect& target) {
-                bool override_movement = false;
-                if (ws == WS_NORMAL || ws == WS_ESSENTIAL)
-                    override_movement = rect_contains(workr, x, y) && rect_eq(target, home) && symptomatic;
-                if (!can_move && !override_movement) return;
-                if (ws != WS_NA) {
-                    int px, py;
-                    random_point(dr, target, px, py);
-                    if (mv.vacant(px, py)) { tx = px; ty = py; }
-                } else {
-                    walk(mv, dr, cur0, can_move, x, y, tx, ty);
-                }
-            };
-            if (ws == WS_NORMAL || ws == WS_ESSENTIAL) {
+            int mode = MODE_WALK;
+            bool dynamics = true, override_movement = false;
+            if (ws == WS_NA) {
+                if (h == 8) kind = AK_HOUSING;
+                else if (h == 12) kind = AK_HOME;
+            } else if (ws != WS_STAFF) {  // Normal | Essential
                 if (h == 7 || h == 17) {
-                    if (s & ST_PT) { goto_area(P.transport); kind = AK_TRANSPORT; }
-                    else walk(mv, dr, cur0, can_move, x, y, tx, ty);
-                } else if (h == 8) { goto_area(workr); kind = AK_WORK; }
-                else if (h == 16) { goto_area(home); kind = AK_HOME; }
-                else walk(mv, dr, cur0, can_move, x, y, tx, ty);
-            } else if (ws == WS_NA) {
-                if (h == 8) { goto_area(P.housing); kind = AK_HOUSING; }
-                else if (h == 12) { goto_area(home); kind = AK_HOME; }
-                else walk(mv, dr, cur0, can_move, x, y, tx, ty);
-            } else {  // HospitalStaff { work_start_at }
-                uint32_t wsa = D.wsa[i];
+                    if (s0 & ST_PT) { mode = MODE_GOTO; R = P.transport; kind = AK_TRANSPORT; }
+                } else if (h == 8) { mode = MODE_GOTO; R = workr; kind = AK_WORK; }
+                else if (h == 16) {
+                    mode = MODE_GOTO; R = home; kind = AK_HOME;
+                    override_movement = symptomatic && rect_contains(workr, x, y);  // citizen/mod.rs:373-381
+                }
+            } else {  // HospitalStaff { work_start_at } (0.14 % of agents)
+                const uint32_t wsa = D.wsa[i];
                 const uint32_t since = hour >= wsa ? hour - wsa : 0u;  // saturating_sub
-                if (since == 24u * 14u) { s |= ST_WQ; dynamics = false; }
+                const uint32_t hosp_kind = P.hospital_gen ? AK_HOSPITAL1 : AK_HOSPITAL0;
+                if (since == 24u * 14u) { s |= ST_WQ; dynamics = false; mode = MODE_STAY; }
                 else if (since == 24u * 14u * 2u) {
-                    goto_area(home); kind = AK_HOME;
+                    mode = MODE_GOTO; R = home; kind = AK_HOME;
                     D.wsa[i] = hour + 24u * 14u;
                     dynamics = false;
                 } else if (h == 8) {
-                    const Rect hr = P.hospital[P.hospital_gen];
-                    if (!rect_eq(cur0, hr) && wsa <= hour) {
-                        goto_area(hr); kind = P.hospital_gen ? AK_HOSPITAL1 : AK_HOSPITAL0;
+                    mode = MODE_STAY;
+                    if (kind0 != hosp_kind && wsa <= hour) {
+                        mode = MODE_GOTO; R = P.hospital[P.hospital_gen]; kind = hosp_kind;
                         D.wsa[i] = hour;
                     }
                     s &= ~ST_WQ;
-                } else if (h == 16) { s |= ST_WQ; }
-                else if (!(s & ST_WQ) && can_move) walk(mv, dr, cur0, can_move, x, y, tx, ty);
+                } else if (h == 16) { s |= ST_WQ; mode = MODE_STAY; }
+                else if (s0 & ST_WQ) mode = MODE_STAY;
             }
+            if (!(can_move || override_movement)) mode = MODE_STAY;
             s = (s & ~ST_AREA_MASK) | (kind << ST_AREA_SHIFT);
+
+            const bool in_area = rect_contains(R, x, y);
+            const bool need_point = mode == MODE_GOTO || (mode == MODE_WALK && !in_area);
+            const bool pre = state == ST_I && sev == SEV_PRE;
+            uint32_t pick = 0, factor = 0;
+            uint64_t a = 0;
+            if (mode == MODE_WALK || (dynamics && (state == ST_E || pre))) dr.common(pick, factor, a);
+            int bx = x, by = y;
+            if (need_point) dr.point(R, bx, by);
+            const bool scan = dynamics && state == ST_S && !(s & (ST_WQ | ST_VACC));
+            int ddx = 0, ddy = 0;  // proposed cell relative to the window centre (bx, by)
+            Window win;
+            if (mode != MODE_STAY || scan) win = load_window(grid, P.pitch, bx, by);
+            if (mode == MODE_GOTO) {
+                if ((uint8_t)(win.w[2] >> 16) == 0) { tx = bx; ty = by; }  // target.get_random_point vacant -> go (citizen/mod.rs:387-392)
+            } else if (mode == MODE_WALK) {  // Citizen::move_agent_from (citizen/mod.rs:415-432)
+                const Hood hd = hood_at(win, 0, 0);
+                const uint32_t vacant = mask_of(__vcmpeq4(hd.lo, 0u), __vcmpeq4(hd.hi, 0u));
+                const uint32_t cand = vacant & valid_mask(R, P.grid_size, bx, by);
+                if (cand) {
+                    const int j = select_bit(cand, mulhi32(pick, (uint32_t)__popc(cand)));
+                    ddx = hood_dx(j); ddy = hood_dy(j);
+                    tx = bx + ddx; ty = by + ddy;
+                }
+            }
             if (dynamics) {
                 // DiseaseStateMachine::next at the proposed cell (disease_state_machine.rs:53-70)
                 if (state == ST_S) {
-                    if (!(s & (ST_WQ | ST_VACC))) {  // on_susceptible, default_disease_handler.rs:64-86
-                        const Rect cur = kind == kind0 ? cur0 : rect_of(kind);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const int nx = tx + c_dx[j], ny = ty + c_dy[j];
-                            if (!(rect_contains(cur, nx, ny) && mv.in_grid(nx, ny))) continue;
-                            const uint32_t b = D.grid[(size_t)ny * P.pitch + (size_t)nx];
-                            if (b >= 2u && bernoulli(dr.get(SLOT_EXPOSE0 + j), P.thr_rate[b - 1u])) {
+                    if (scan) {  // on_susceptible, default_disease_handler.rs:64-86
+                        // the proposed cell is the window centre + (ddx, ddy), or the agent's own cell when the move
+                        // was not possible: a relocated walker / a goto that found its point occupied stays at (x, y),
+                        // which is outside the window -> rare second load
+                        Hood hd;
+                        if (tx == bx + ddx && ty == by + ddy) hd = hood_at(win, ddx, ddy);
+                        else hd = hood_at(load_window(grid, P.pitch, tx, ty), 0, 0);
+                        uint32_t inf = mask_of(__vcmpgeu4(hd.lo, 0x02020202u), __vcmpgeu4(hd.hi, 0x02020202u));
+                        // neighbours are clipped to the NEW current_area: R is its rectangle unless a non-working agent's
+                        // area changed this hour (h = 8, 12), where R is still the old one
+                        if (inf) inf &= valid_mask(kind == kind0 ? R : rect_of(kind), P.grid_size, tx, ty);
+                        while (inf) {
+                            const int j = __ffs(inf) - 1;
+                            inf &= inf - 1u;
+                            const uint32_t b = ((j < 4 ? hd.lo : hd.hi) >> (8 * (j & 3))) & 0xFFu;
+                            if (bernoulli(dr.expose(j), P.thr_rate[b - 1u])) {
                                 state = ST_E;
                                 D.t0[i] = hour;
                                 break;
@@ -270,18 +344,15 @@ __global__ void __launch_bounds__(256) k_hour(Params P, DevPtrs D, uint32_t hour
                         }
                     }
                 } else if (state == ST_E) {  // on_exposed, :52-62
-                    uint64_t da, db_unused;
-                    dr.pair(SLOT_PICK, db_unused, da);  // slot 3 = high pair of block 1
-                    const int f = (int)mulhi64(da, 3ull) - 1;
+                    const int f = (int)mulhi32(factor, 3u) - 1;
                     if (hour - D.t0[i] >= (uint32_t)((int)P.exposed_duration + f)) {
-                        const bool symptoms = bernoulli(dr.get(SLOT_B), P.thr_symptomatic);
+                        const bool symptoms = bernoulli(a, P.thr_symptomatic);
                         state = ST_I; day = 0;
                         sev = symptoms ? SEV_PRE : SEV_ASYM;
                         if (symptoms) D.t0[i] = hour;
                     }
-                } else if (state == ST_I) {  // on_infected, :41-50
-                    if (sev == SEV_PRE && hour - D.t0[i] >= P.pre_symptomatic_duration)
-                        sev = bernoulli(dr.get(SLOT_A), P.thr_severe) ? SEV_SEVERE : SEV_MILD;
+                } else if (pre) {  // on_infected, :41-50
+                    if (hour - D.t0[i] >= P.pre_symptomatic_duration) sev = bernoulli(a, P.thr_severe) ? SEV_SEVERE : SEV_MILD;
                 }
             }
         }
@@ -308,12 +379,12 @@ __global__ void __launch_bounds__(256) k_commit(Params P, DevPtrs D, uint32_t ho
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n) return;
     const uint32_t prop = D.prop[i];
+    const uint32_t c0 = D.cell[i];  // issued with the prop load: one memory round trip
+    const uint32_t hour = D.clock->hour_base + hour_offset;
     if (prop == 0) return;
     const uint32_t byte = (prop >> PROP_BYTE_SHIFT) + 1u;
-    const uint32_t c0 = D.cell[i];
     size_t at = (size_t)(c0 >> CELL_BITS) * P.pitch + (c0 & CELL_XMASK);
     if (prop & PROP_MOVE) {
-        const uint32_t hour = D.clock->hour_base + hour_offset;
         const uint32_t stamp = hour - D.clock->epoch_base + 1u;
         const uint32_t id_mask = (1u << P.id_bits) - 1u;
         const uint32_t tc = prop & PROP_CELL_MASK;
@@ -372,7 +443,7 @@ __global__ void __launch_bounds__(256) k_build_grid(Params P, const uint32_t* __
     if (i >= P.n) return;
     const uint32_t c = cell[i];
     const size_t at = (size_t)(c >> CELL_BITS) * P.pitch + (c & CELL_XMASK);
-    // byte-wide check-and-set through the containing word
+    // byte-wide check-and-set through the containing word (grid base and pitch are 4-byte aligned)
     uint32_t* word = (uint32_t*)(grid + (at & ~(size_t)3));
     const uint32_t shift = (uint32_t)(at & 3) * 8u;
     const uint32_t old = atomicOr(word, cell_byte(P, st[i]) << shift);
@@ -390,9 +461,16 @@ void launch_hospital_scan(const Params& P, const DevPtrs& D, cudaStream_t s) {
     if (blocks == 0) blocks = 1;
     k_hospital_scan<<<blocks, 256, 0, s>>>(P, D.grid, D.hosp_first);
 }
-void launch_hour(const Params& P, const DevPtrs& D, uint32_t hour_offset, bool inject, cudaStream_t s) {
-    if (inject) k_hour<true><<<blocks_for(P.n), 256, 0, s>>>(P, D, hour_offset);
-    else k_hour<false><<<blocks_for(P.n), 256, 0, s>>>(P, D, hour_offset);
+template <bool INJECT>
+static void launch_hour_t(const Params& P, const DevPtrs& D, uint32_t hour_of_day, uint32_t hour_offset, cudaStream_t s) {
+    const unsigned b = blocks_for(P.n);
+    if (hour_of_day == 0) k_hour<KIND_START, INJECT><<<b, 256, 0, s>>>(P, D, hour_offset);
+    else if (hour_of_day == 23) k_hour<KIND_END, INJECT><<<b, 256, 0, s>>>(P, D, hour_offset);
+    else k_hour<KIND_MOVE, INJECT><<<b, 256, 0, s>>>(P, D, hour_offset);
+}
+void launch_hour(const Params& P, const DevPtrs& D, uint32_t hour_of_day, uint32_t hour_offset, bool inject, cudaStream_t s) {
+    if (inject) launch_hour_t<true>(P, D, hour_of_day, hour_offset, s);
+    else launch_hour_t<false>(P, D, hour_of_day, hour_offset, s);
 }
 void launch_set_clock(Clock* clock, const Clock& value, cudaStream_t s) { k_set_clock<<<1, 1, 0, s>>>(clock, value); }
 void launch_commit(const Params& P, const DevPtrs& D, uint32_t hour_offset, cudaStream_t s) { k_commit<<<blocks_for(P.n), 256, 0, s>>>(P, D, hour_offset); }

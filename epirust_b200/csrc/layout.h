@@ -4,11 +4,14 @@
 //   cell[N] u32   packed (y << 14) | x of the cell the agent stands on          (reference: the map key Point)
 //   st[N]   u32   packed Citizen fields, layout below                          (citizen/mod.rs:48-63)
 //   t0[N]   u32   at_hour of State::Exposed / Severity::Pre                     (state_machine/state.rs:22-37)
-//   home[N] u32   house index  | home region << 24                             (Citizen.home_location)
-//   work[N] u32   office index | work region << 24 (unused for WorkStatus::NA)  (Citizen.work_location)
+//   home[N] u32   packed (sy << 14) | sx origin of the agent's 2x2 house          (Citizen.home_location)
+//   work[N] u32   packed origin of the agent's 10x10 office (unused for WorkStatus::NA)  (Citizen.work_location)
+//                 (origins instead of indices: no div/mod in the hot kernel; the C ABI speaks house/office indices)
 //   wsa[N]  u32   WorkStatus::HospitalStaff.work_start_at (0.14 % of agents)    (citizen/work_status.rs:26)
 //   prop[N] u32   this hour's proposal, hour kernel -> commit kernel
-// Per cell (pitch = grid_size + 1 columns, rows = grid_size + 1; y-major so x neighbours are adjacent bytes):
+// Per cell (pitch >= grid_size + 2 columns, rows = grid_size + 1; y-major so x neighbours are adjacent bytes; the
+// allocation carries GRID_YPAD padding rows above and below and GRID_XPAD bytes left of row 0, always zero, so the 5x5
+// window around any cell can be loaded without bounds checks):
 //   grid[cells]  u8   0 vacant, 1 occupied & not infectious, 2 occupied & regular-rate, 3 occupied & high-rate
 //                     (replaces AgentLocationMap / FnvHashMap<Point, Citizen>, allocation_map.rs:44-49: vacancy and
 //                      the neighbour's transmission rate are the only things other agents read from a cell)
@@ -51,8 +54,9 @@ constexpr uint32_t PROP_DIRTY = 1u << 29;  // the agent's grid byte changed
 constexpr int PROP_BYTE_SHIFT = 30;        // new grid byte - 1
 
 constexpr uint32_t HOSP_NONE = 0xFFFFFFFFu;
-constexpr uint32_t REGION_SHIFT = 24;
-constexpr uint32_t INDEX_MASK = (1u << REGION_SHIFT) - 1;
+constexpr uint32_t ORIGIN_MASK = (1u << 28) - 1;  // home / work words: packed origin in the low 28 bits
+constexpr uint32_t GRID_XPAD = 16;                // zero bytes before the start of row 0 in the grid allocation
+constexpr uint32_t GRID_YPAD = 3;                 // zero rows above row 0 and below the last row
 
 struct Rect {
     int sx, sy, ex, ey;  // inclusive on both ends (geography/area.rs:83-88)

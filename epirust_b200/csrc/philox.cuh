@@ -1,7 +1,14 @@
 // Philox4x32-10 counter-based RNG (Salmon, Moraes, Dror, Shaw: "Parallel random numbers: as easy as 1, 2, 3", SC'11).
-// Every draw on the hot path is philox(key = seed, counter = (agent, hour, slot/2, domain)) -- no sequential RNG state,
+// Every draw on the hot path is philox(key = seed, counter = (agent, hour, block, domain)) -- no sequential RNG state,
 // so any thread can compute any agent's draw (BASELINE.json north_star: "(seed, agent, hour, draw)").
 // Replaces common::utils::RandomWrapper / rand::thread_rng (common/src/utils/random_wrapper.rs:23-35).
+//
+// Hour-step draws (DOM_STEP) -- one block serves the common agent-hour:
+//   block 0: x = PICK (u32)  y = FACTOR (u32)  z,w = A (u64)
+//   block 1: x = PX (u32)    y = PY (u32)
+//   block 2+(j>>1): EXPOSE j (u64) = x,y for even j, z,w for odd j   (j = 0..7, Moore neighbour order)
+// Injected-draw tables (epi_step_with_draws) carry 16 u64 per agent indexed by the slot numbers below; u32 draws take
+// the low 32 bits.  All other domains use generic u64 slots: slot s = block s>>1, x,y for even s, z,w for odd s.
 #pragma once
 #include <stdint.h>
 
@@ -51,11 +58,15 @@ EPI_HD U4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint
 
 // draw domains (4th counter word)
 enum : uint32_t { DOM_STEP = 0, DOM_INIT = 1, DOM_VACCINATE = 2, DOM_MIGRATE = 3, DOM_STARTINF = 4, DOM_ARRIVAL = 5 };
+// hour-step slot numbers (index into an injected-draw row)
+enum : uint32_t { SLOT_PICK = 0, SLOT_FACTOR = 1, SLOT_A = 2, SLOT_PX = 3, SLOT_PY = 4, SLOT_EXPOSE0 = 8 };
 
-// one 64-bit draw: slot s lives in block s>>1, low pair for even slots, high pair for odd slots
+EPI_HD uint64_t u64_of(uint32_t lo, uint32_t hi) { return (uint64_t)lo | ((uint64_t)hi << 32); }
+
+// generic u64 slot of a non-step domain
 EPI_HD uint64_t philox_draw(uint64_t seed, uint32_t agent, uint32_t hour, uint32_t domain, uint32_t slot) {
     const U4 o = philox4x32_10(agent, hour, slot >> 1, domain, (uint32_t)seed, (uint32_t)(seed >> 32));
-    return (slot & 1u) ? ((uint64_t)o.z | ((uint64_t)o.w << 32)) : ((uint64_t)o.x | ((uint64_t)o.y << 32));
+    return (slot & 1u) ? u64_of(o.z, o.w) : u64_of(o.x, o.y);
 }
 
 // rand 0.8 `Rng::gen_bool(p)`: Bernoulli::new(p) -> p == 1.0 always true, else p_int = (p * 2^64) as u64, sample u64 < p_int.

@@ -95,23 +95,35 @@ inline void philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-// Draw domains (4th counter word) and per-agent-hour slot numbers.  This is the
+// Draw domains (4th counter word) and per-agent-hour draw slots.  This is the
 // (seed, agent, hour, draw) convention of BASELINE.json north_star; DESIGN.md
 // section "Draw slots" is the normative statement, restated here and in the kernels.
+//
+// Hour-step draws (DOM_STEP) are laid out so that the common agent-hour needs ONE
+// Philox4x32 block (counter = (agent, hour, block, DOM_STEP)):
+//   block 0: word0 = PICK (u32)  word1 = FACTOR (u32)  words2,3 = A (u64)
+//   block 1: word0 = PX (u32)    word1 = PY (u32)
+//   block 2+(j>>1): EXPOSE j (u64) = words 0,1 for even j, words 2,3 for odd j   (j = 0..7)
+// u32 draws feed uniform-integer choices (index = mulhi32(draw, n), like rand 0.8's
+// 32-bit widening-multiply sampler without the negligible rejection zone), u64 draws
+// feed Bernoulli trials (draw < p * 2^64, exactly rand 0.8's Bernoulli).
+// Every other domain (init, vaccinate, ...) uses generic u64 slots: slot s = block s>>1,
+// words 0,1 for even s, words 2,3 for odd s.
 enum Domain : uint32_t { DOM_STEP = 0, DOM_INIT = 1, DOM_VACCINATE = 2, DOM_MIGRATE = 3, DOM_STARTINF = 4, DOM_ARRIVAL = 5 };
 enum Slot : uint32_t {
-    SLOT_PX = 0,      // Area::get_random_point x   (area.rs:77)
-    SLOT_PY = 1,      // Area::get_random_point y   (area.rs:78)
-    SLOT_PICK = 2,    // move_agent_from neighbour choose (citizen/mod.rs:430)
-    SLOT_A = 3,       // on_exposed factor / on_infected severe / is_to_be_deceased
-    SLOT_B = 4,       // on_exposed symptomatic
-    SLOT_EXPOSE0 = 8  // +j : gen_bool(rate of Moore neighbour j), j=0..7 (default_disease_handler.rs:79)
+    SLOT_PICK = 0,    // move_agent_from neighbour choose (citizen/mod.rs:430)                       u32
+    SLOT_FACTOR = 1,  // on_exposed RANGE_FOR_EXPOSED.choose (default_disease_handler.rs:53)          u32
+    SLOT_A = 2,       // on_exposed symptomatic / on_infected severe / is_to_be_deceased              u64
+    SLOT_PX = 3,      // Area::get_random_point x   (area.rs:77)                                      u32
+    SLOT_PY = 4,      // Area::get_random_point y   (area.rs:78)                                      u32
+    SLOT_EXPOSE0 = 8  // +j : gen_bool(rate of Moore neighbour j), j=0..7 (default_disease_handler.rs:79)  u64
 };
 const int SLOTS_PER_AGENT = 16;
 // init slots (DOM_INIT, hour word = 0)
 enum InitSlot : uint32_t { IS_WORKING = 0, IS_PT = 1, IS_STAFF = 2, IS_IMMUNITY = 3, IS_ESSENTIAL = 4, IS_STARTX = 5, IS_STARTY = 6 };
 
 inline uint64_t mulhi64(uint64_t a, uint64_t b) { return (uint64_t)(((unsigned __int128)a * b) >> 64); }
+inline uint32_t mulhi32(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
 
 // rand 0.8 Bernoulli::new(p): p==1.0 -> always true, else p_int = (p * 2^64) as u64; sample: u64 < p_int
 inline uint64_t bernoulli_threshold(double p) {
@@ -131,17 +143,45 @@ struct Rng {
     // STREAM
     std::mt19937_64* stream = nullptr;
 
+    void block(uint32_t b, uint32_t o[4]) const {
+        uint32_t ctr[4] = {agent, hour, b, domain};
+        uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+        philox4x32_10(ctr, key, o);
+    }
+    // a u64 draw
     uint64_t next(uint32_t slot) {
         switch (mode) {
             case KEYED: {
-                uint32_t ctr[4] = {agent, hour, slot >> 1, domain};
-                uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
                 uint32_t o[4];
-                philox4x32_10(ctr, key, o);
+                if (domain == DOM_STEP) {
+                    if (slot == SLOT_A) { block(0, o); return (uint64_t)o[2] | ((uint64_t)o[3] << 32); }
+                    if (slot < SLOT_EXPOSE0 || slot >= SLOT_EXPOSE0 + 8) throw std::logic_error("not a u64 step slot");
+                    const uint32_t j = slot - SLOT_EXPOSE0;
+                    block(2 + (j >> 1), o);
+                    return (j & 1) ? ((uint64_t)o[2] | ((uint64_t)o[3] << 32)) : ((uint64_t)o[0] | ((uint64_t)o[1] << 32));
+                }
+                block(slot >> 1, o);
                 return (slot & 1) ? ((uint64_t)o[2] | ((uint64_t)o[3] << 32)) : ((uint64_t)o[0] | ((uint64_t)o[1] << 32));
             }
             case TABLE: return row[slot];
             default: return (*stream)();
+        }
+    }
+    // a u32 draw (hour-step domain only)
+    uint32_t next32(uint32_t slot) {
+        switch (mode) {
+            case KEYED: {
+                uint32_t o[4];
+                switch (slot) {
+                    case SLOT_PICK: block(0, o); return o[0];
+                    case SLOT_FACTOR: block(0, o); return o[1];
+                    case SLOT_PX: block(1, o); return o[0];
+                    case SLOT_PY: block(1, o); return o[1];
+                    default: throw std::logic_error("not a u32 step slot");
+                }
+            }
+            case TABLE: return (uint32_t)row[slot];
+            default: return (uint32_t)((*stream)() >> 32);
         }
     }
     // rand::Rng::gen_bool
@@ -150,10 +190,12 @@ struct Rng {
         if (thr == UINT64_MAX) return true;  // Bernoulli ALWAYS_TRUE consumes no draw
         return next(slot) < thr;
     }
-    // rand::Rng::gen_range(a..=b) : uniform integer
+    // rand::Rng::gen_range(a..=b) : uniform integer.  64-bit flavour (init domains) and 32-bit flavour (hour step)
     int gen_range_incl(uint32_t slot, int a, int b) { return a + (int)mulhi64(next(slot), (uint64_t)(b - a + 1)); }
+    int gen_range_incl32(uint32_t slot, int a, int b) { return a + (int)mulhi32(next32(slot), (uint32_t)(b - a + 1)); }
     // SliceRandom::choose / IteratorRandom::choose over n candidates : uniform index
     uint32_t choose_index(uint32_t slot, uint32_t n) { return (uint32_t)mulhi64(next(slot), n); }
+    uint32_t choose_index32(uint32_t slot, uint32_t n) { return mulhi32(next32(slot), n); }
 };
 
 // -----------------------------------------------------------------------------
@@ -191,8 +233,8 @@ struct Area {
     }
     // area.rs:76-81
     Point get_random_point(Rng& rng) const {
-        int rx = rng.gen_range_incl(SLOT_PX, start_offset.x, end_offset.x);
-        int ry = rng.gen_range_incl(SLOT_PY, start_offset.y, end_offset.y);
+        int rx = rng.gen_range_incl32(SLOT_PX, start_offset.x, end_offset.x);
+        int ry = rng.gen_range_incl32(SLOT_PY, start_offset.y, end_offset.y);
         return Point{rx, ry};
     }
     // area.rs:90-92 (sic: (ex-sx)*(ey-sy), not the inclusive cell count)
@@ -568,9 +610,9 @@ inline bool on_infected(const Disease& d, Hour sim_hr, const State& cur, Rng& rn
 }
 // :52-62
 inline bool on_exposed(const Disease& d, Hour at_hour, Hour sim_hr, Rng& rng, State& out) {
-    int random_factor = constants::RANGE_FOR_EXPOSED[rng.choose_index(SLOT_A, 3)];
+    int random_factor = constants::RANGE_FOR_EXPOSED[rng.choose_index32(SLOT_FACTOR, 3)];
     if (sim_hr - at_hour >= (Hour)((int32_t)d.exposed_duration + random_factor)) {
-        bool symptoms = rng.gen_bool(SLOT_B, 1.0 - d.percentage_asymptomatic_population);
+        bool symptoms = rng.gen_bool(SLOT_A, 1.0 - d.percentage_asymptomatic_population);
         out = symptoms ? State::infected(0, Pre, sim_hr) : State::infected(0, Asymptomatic);
         return true;
     }
@@ -754,7 +796,7 @@ inline Point Citizen::move_agent_from(const CitizenLocationMap& map, Point cell,
     for (int j = 0; j < n; ++j)
         if (map.is_point_in_grid(nb[j]) && map.is_cell_vacant(nb[j])) cand[k++] = nb[j];
     Point new_cell = cell;  // .unwrap_or(cell)
-    if (k > 0) new_cell = cand[rng.choose_index(SLOT_PICK, (uint32_t)k)];
+    if (k > 0) new_cell = cand[rng.choose_index32(SLOT_PICK, (uint32_t)k)];
     return map.move_agent(cell, new_cell);
 }
 

@@ -153,6 +153,10 @@ uint64_t orc_kat_draw(uint64_t seed, uint32_t agent, uint32_t hour, uint32_t dom
     Rng r; r.mode = Rng::KEYED; r.seed = seed; r.agent = agent; r.hour = hour; r.domain = domain;
     return r.next(slot);
 }
+uint32_t orc_kat_draw32(uint64_t seed, uint32_t agent, uint32_t hour, uint32_t slot) {
+    Rng r; r.mode = Rng::KEYED; r.seed = seed; r.agent = agent; r.hour = hour; r.domain = DOM_STEP;
+    return r.next32(slot);
+}
 uint64_t orc_kat_bernoulli_threshold(double p) { return bernoulli_threshold(p); }
 void orc_kat_neighbors(int x, int y, int32_t* out16) {
     for (int j = 0; j < 8; ++j) { out16[2 * j] = x + NEIGHBOR_OFFSETS[j][0]; out16[2 * j + 1] = y + NEIGHBOR_OFFSETS[j][1]; }

@@ -134,6 +134,8 @@ def lib():
         L.orc_time_hours.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
         L.orc_kat_draw.restype = C.c_uint64
         L.orc_kat_draw.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
+        L.orc_kat_draw32.restype = C.c_uint32
+        L.orc_kat_draw32.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32]
         L.orc_kat_bernoulli_threshold.restype = C.c_uint64
         L.orc_kat_bernoulli_threshold.argtypes = [C.c_double]
         L.orc_kat_number_of_cells.restype = C.c_uint32

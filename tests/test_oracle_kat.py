@@ -32,15 +32,30 @@ def test_philox_known_answers(L):
 
 
 def test_draw_slot_convention(L):
-    # slot s lives in Philox block s>>1 of counter (agent, hour, s>>1, domain); even slot = words 0,1; odd = words 2,3
-    seed, agent, hour, dom = 0x1234_5678_9ABC_DEF0, 77, 31, 0
-    for slot in range(16):
-        ctr = np.array([agent, hour, slot >> 1, dom], np.uint32)
-        key = np.array([seed & 0xFFFFFFFF, seed >> 32], np.uint32)
+    seed, agent, hour = 0x1234_5678_9ABC_DEF0, 77, 31
+    key = np.array([seed & 0xFFFFFFFF, seed >> 32], np.uint32)
+
+    def block(b, dom):
         out = np.zeros(4, np.uint32)
-        L.orc_kat_philox(_p(ctr), _p(key), _p(out))
-        lo, hi = (out[2], out[3]) if slot & 1 else (out[0], out[1])
-        assert L.orc_kat_draw(seed, agent, hour, dom, slot) == int(lo) | (int(hi) << 32)
+        L.orc_kat_philox(_p(np.array([agent, hour, b, dom], np.uint32)), _p(key), _p(out))
+        return [int(v) for v in out]
+
+    # generic domains: u64 slot s lives in Philox block s>>1 of counter (agent, hour, s>>1, domain); even = words 0,1; odd = words 2,3
+    for slot in range(16):
+        o = block(slot >> 1, 1)
+        lo, hi = (o[2], o[3]) if slot & 1 else (o[0], o[1])
+        assert L.orc_kat_draw(seed, agent, hour, 1, slot) == lo | (hi << 32)
+    # hour-step domain: block 0 = PICK, FACTOR, A ; block 1 = PX, PY ; block 2+(j>>1) = EXPOSE j
+    o0, o1 = block(0, 0), block(1, 0)
+    assert L.orc_kat_draw32(seed, agent, hour, 0) == o0[0]  # SLOT_PICK
+    assert L.orc_kat_draw32(seed, agent, hour, 1) == o0[1]  # SLOT_FACTOR
+    assert L.orc_kat_draw(seed, agent, hour, 0, 2) == o0[2] | (o0[3] << 32)  # SLOT_A
+    assert L.orc_kat_draw32(seed, agent, hour, 3) == o1[0]  # SLOT_PX
+    assert L.orc_kat_draw32(seed, agent, hour, 4) == o1[1]  # SLOT_PY
+    for j in range(8):
+        o = block(2 + (j >> 1), 0)
+        lo, hi = (o[2], o[3]) if j & 1 else (o[0], o[1])
+        assert L.orc_kat_draw(seed, agent, hour, 0, 8 + j) == lo | (hi << 32)
 
 
 def test_bernoulli_threshold_is_rand_0_8(L):

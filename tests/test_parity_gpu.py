@@ -48,7 +48,7 @@ def test_hour_by_hour_bit_exact(seed):
 
 def test_dense_epidemic_with_fast_disease():
     # high rates and short durations so every transition (S->E->I->R/D, hospitalisation, hospital-full) happens often
-    kw = dict(n_agents=6000, grid_size=100, exposed=200, severe=100, mild=50, asym=50, beds=0.0005,
+    kw = dict(n_agents=3600, grid_size=100, exposed=200, severe=100, mild=50, asym=50, beds=0.0005,
               regular_transmission_rate=0.6, high_transmission_rate=0.9, death_rate=0.4, exposed_duration=10, pre_symptomatic_duration=8,
               last_day=6, regular_transmission_start_day=1, high_transmission_start_day=3, percentage_severe_infected_population=0.6)
     gc, oc = small_cfg(**kw)
@@ -75,8 +75,8 @@ def test_substep_with_injected_draws(hour):
             gpu.step(h), orc.step(h)
         draws = rng.integers(0, 2**64, size=(gpu.population, 16), dtype=np.uint64)
         # make Bernoulli successes common so transitions fire
-        draws[:, 3:5] >>= np.uint64(rng.integers(0, 3))
-        draws[:, 8:16] >>= np.uint64(2)
+        draws[:, 2] >>= np.uint64(rng.integers(0, 3))  # SLOT_A (u64 Bernoulli draw)
+        draws[:, 8:16] >>= np.uint64(2)  # SLOT_EXPOSE0..7
         cg, co = gpu.step(hour, draws), orc.step(hour, draws)
         assert (cg == co).all()
         assert_state_equal(gpu, orc, f"injected hour {hour}")
