@@ -10,7 +10,7 @@ LIB_PATH = os.path.join(PKG, "libepirust_b200.so")
 
 EPI_DRAWS_PER_AGENT = 16
 EPI_N_KERNEL_KINDS = 8
-KERNEL_KINDS = ("hour", "commit", "hospital_scan", "sleep", "sweep", "pack", "unpack", "misc")
+KERNEL_KINDS = ("hour", "commit", "hospital_scan", "sleep", "sweep", "spare", "travel", "misc")
 
 
 class EpiConfig(C.Structure):

@@ -32,7 +32,7 @@ int engine_fail(const epi_engine* e, int code, const std::string& msg) {
             return engine_fail(e, EPI_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_err));              \
     } while (0)
 
-enum KernelKind { KK_HOUR = 0, KK_COMMIT = 1, KK_SCAN = 2, KK_SLEEP = 3, KK_SWEEP = 4, KK_PACK = 5, KK_UNPACK = 6, KK_MISC = 7 };
+enum KernelKind { KK_HOUR = 0, KK_COMMIT = 1, KK_SCAN = 2, KK_SLEEP = 3, KK_SWEEP = 4, KK_SPARE = 5, KK_TRAVEL = 6, KK_MISC = 7 };
 
 namespace {
 
@@ -93,6 +93,13 @@ int rebuild_grid(epi_engine* e) {
     CU(cudaStreamSynchronize(e->stream));
     if (collisions) return engine_fail(e, EPI_ERR_STATE, "two agents on one cell (" + std::to_string(collisions) + " collisions)");
     e->claim_dirty = true;
+    // running Counts totals: absolute recount into copy 0
+    CU(cudaMemsetAsync(e->D.tot, 0, (size_t)TOT_COPIES * 8 * sizeof(uint32_t), e->stream));
+    {
+        Timed t(e, KK_MISC);
+        launch_recount(e->P, e->D, e->stream);
+    }
+    e->have_last_row = false;
     return EPI_OK;
 }
 
@@ -217,8 +224,19 @@ int run_chunk(epi_engine* e, uint32_t first_hour, uint32_t n, bool inject, epi_c
     CU(cudaStreamSynchronize(e->stream));
     if (e->timing) drain_events(e);
     for (uint32_t k = 0; k < n; ++k) {
-        if (ran[k]) row_to_counts(e->h_counts + (size_t)k * 8, first_hour + k, &e->last_counts);
-        else e->last_counts.hour = first_hour + k;  // sleep hour: nothing observable changed (citizen/mod.rs:244-248)
+        if (ran[k]) {
+            const epi_counts prev = e->last_counts;
+            row_to_counts(e->h_counts + (size_t)k * 8, first_hour + k, &e->last_counts);
+            const uint32_t h = (first_hour + k) % 24u;
+            if (h >= 1 && h <= 6 && e->have_last_row) {
+                // k_sleep recounts every agent; the previous row came from the incrementally tracked totals: they must agree
+                const epi_counts& c = e->last_counts;
+                if (c.susceptible != prev.susceptible || c.exposed != prev.exposed || c.infected != prev.infected ||
+                    c.hospitalized != prev.hospitalized || c.recovered != prev.recovered || c.deceased != prev.deceased)
+                    return engine_fail(e, EPI_ERR_STATE, "incrementally tracked Counts diverged from the recount at hour " + std::to_string(first_hour + k));
+            }
+            e->have_last_row = true;
+        } else e->last_counts.hour = first_hour + k;  // sleep hour: nothing observable changed (citizen/mod.rs:244-248)
         out[k] = e->last_counts;
         const uint64_t total = (uint64_t)out[k].susceptible + out[k].exposed + out[k].infected + out[k].hospitalized + out[k].recovered + out[k].deceased;
         if (total != e->P.n)  // allocation_map.rs:128 assert_eq!(csv_record.total(), current_population)
@@ -317,6 +335,7 @@ int epi_create_region(const epi_config* cfg, uint64_t seed, int device, int regi
         e->D.grid = e->grid_alloc ? e->grid_alloc + (size_t)e->geo.pitch * GRID_YPAD + GRID_XPAD : nullptr;
         ok &= dev_alloc(e, &e->D.claim, cells) == cudaSuccess;
         ok &= dev_alloc(e, &e->D.counts, (size_t)RING_ROWS * 8) == cudaSuccess;
+        ok &= dev_alloc(e, &e->D.tot, (size_t)TOT_COPIES * 8) == cudaSuccess;
         ok &= dev_alloc(e, &e->d_clock, 1) == cudaSuccess;
         ok &= dev_alloc(e, &e->d_misc, 4) == cudaSuccess;
         ok &= dev_alloc(e, &e->i_cell, n) == cudaSuccess;
@@ -351,7 +370,7 @@ void epi_destroy(epi_engine* e) {
     if (e->stream) cudaStreamSynchronize(e->stream);
     drop_graph(e);
     for (auto& pe : e->pending_events) { cudaEventDestroy(pe.second.first); cudaEventDestroy(pe.second.second); }
-    void* ptrs[] = {e->D.cell, e->D.st, e->D.t0, e->D.home, e->D.work, e->D.wsa, e->D.prop, e->grid_alloc, e->D.claim, e->D.counts,
+    void* ptrs[] = {e->D.cell, e->D.st, e->D.t0, e->D.home, e->D.work, e->D.wsa, e->D.prop, e->grid_alloc, e->D.claim, e->D.counts, e->D.tot,
                     e->d_clock, e->d_misc, e->d_draws, e->i_cell, e->i_st, e->i_t0, e->i_home, e->i_work, e->i_wsa};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (e->h_counts) cudaFreeHost(e->h_counts);
@@ -519,7 +538,7 @@ int epi_set_state(epi_engine* e, uint32_t n, const int32_t* cx, const int32_t* c
 
 int epi_geometry(const epi_engine* e, int32_t* out) {
     if (!e || !out) return engine_fail(e, EPI_ERR_ARG, "null argument");
-    const Rect rs[4] = {e->geo.housing, e->geo.transport, e->geo.work, e->P.hospital[e->P.hospital_gen]};
+    const Rect rs[4] = {e->geo.housing, e->geo.transport, e->geo.work, e->P.hospital()};
     for (int i = 0; i < 4; ++i) { out[4 * i] = rs[i].sx; out[4 * i + 1] = rs[i].sy; out[4 * i + 2] = rs[i].ex; out[4 * i + 3] = rs[i].ey; }
     out[16] = (int32_t)e->geo.n_houses; out[17] = (int32_t)e->geo.n_offices; out[18] = e->geo.grid_size;
     return EPI_OK;

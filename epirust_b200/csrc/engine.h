@@ -43,6 +43,7 @@ struct epi_engine {
     std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> pending_events;
     uint64_t launches = 0;
     epi_counts last_counts{};
+    bool have_last_row = false;  // last_counts is the row of the hour just before the next one to run
     // host side of CitizenLocationMap::process_interventions (allocation_map.rs:306-337): the decisions
     epi::Interventions interventions;
     std::vector<epi_intervention_event> events;

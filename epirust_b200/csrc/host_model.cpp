@@ -84,8 +84,8 @@ Params make_params(const epi_config& c, const Geometry& g, uint64_t seed, int re
     P.grid_size = g.grid_size;
     P.pitch = g.pitch;
     P.rows = g.rows;
-    P.housing = g.housing; P.transport = g.transport; P.work = g.work;
-    P.hospital[0] = g.hospital_resized; P.hospital[1] = g.hospital_expanded;
+    P.zone[0] = g.transport; P.zone[1] = g.housing; P.zone[2] = g.hospital_resized; P.zone[3] = g.hospital_expanded;
+    P.work = g.work;
     P.hospital_gen = 0;
     P.house_nx = g.house_nx; P.office_nx = g.office_nx;
     P.regular_start = c.regular_transmission_start_day;
@@ -105,6 +105,10 @@ Params make_params(const epi_config& c, const Geometry& g, uint64_t seed, int re
     while ((1ull << bits) < (uint64_t)P.n) ++bits;
     P.id_bits = bits;
     P.seed = seed;
+    for (uint32_t r = 0; r < 10; ++r) {
+        P.rk[r][0] = (uint32_t)seed + r * 0x9E3779B9u;
+        P.rk[r][1] = (uint32_t)(seed >> 32) + r * 0xBB67AE85u;
+    }
     P.region = region;
     return P;
 }

@@ -4,9 +4,9 @@
 //   k_hour<KIND>      one agent per thread: routine, movement proposal against the start-of-hour grid, disease
 //                     transition, Counts; atomicMax claim on the target cell (citizen/mod.rs:227-432,
 //                     default_disease_handler.rs:31-103, counts.rs:126-140).  KIND: the hour-of-day class
-//                     (0 = ROUTINE_START_TIME, 23 = ROUTINE_END_TIME, else perform_movements) -- uniform per launch.
+//                     (ROUTINE_START_TIME, ROUTINE_END_TIME, else perform_movements) -- uniform per launch.
 //   k_commit          lowest-id claimant moves, loser stays; grid bytes updated in place (allocation_map.rs:93-102,131-134)
-//   k_sleep           hours 1..6: current_area := home (citizen/mod.rs:244-248) + Counts
+//   k_sleep           hours 1..6: current_area := home (citizen/mod.rs:244-248) + Counts recount
 //   k_lock / k_unlock / k_vaccinate   intervention sweeps (allocation_map.rs:349-387)
 //
 // Synchronous-update argument (why the grid can be updated in place): every proposal targets a cell that was vacant
@@ -15,10 +15,16 @@
 // of the hour, so the set of written-to-occupied and written-to-vacant cells are disjoint, and all reads of the grid
 // happen in k_hour, all writes in k_commit.
 //
-// Instruction budget: the kernel is issue-bound before it is HBM-bound, so the agent-hour is written branch-light:
-// the movement rule of the hour is reduced to (mode, rectangle) by predicated integer logic, one Philox block serves
-// the common case, the 3x3 neighbourhood is loaded unconditionally from the zero-padded grid and reduced with
-// byte-SIMD intrinsics.
+// Claim protocol (north_star (b): lowest-agent-id priority): k_hour does atomicMax(claim[cell], stamp | ~id) -- a
+// fire-and-forget reduction, nobody waits for its result; k_commit moves the agent iff claim[cell] is its own word.
+// The hour stamp in the high bits makes clearing the claim array unnecessary.  (A three-phase variant that marks
+// CLAIMED / CONTESTED bits in the occupancy byte and touches claim[] only for contested cells was measured slower:
+// its phase-A atomic needs its return value, and the extra pass costs more than the DRAM traffic it saves.)
+//
+// Instruction budget: k_hour is issue/latency-bound before it is HBM-bound, so the agent-hour is branch-light: the
+// movement rule of the hour is reduced to (mode, rectangle) by predicated integer logic, one Philox block serves the
+// common case, the agent's four state words are loaded up front in one round trip, and one 5x5 window of the
+// zero-padded grid (10 aligned 32-bit loads, one round trip) serves both the walk and the exposure scan.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -30,6 +36,18 @@ namespace epi {
 
 enum : int { MODE_STAY = 0, MODE_WALK = 1, MODE_GOTO = 2 };
 enum : int { KIND_START = 0, KIND_MOVE = 1, KIND_END = 2 };
+
+// a load the compiler may not sink below a branch: all of an agent's words are requested in one memory round trip
+__device__ __forceinline__ uint32_t ld_early(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint32_t ld_early_rw(const uint32_t* p) {  // for arrays this kernel also writes
+    uint32_t v;
+    asm volatile("ld.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
 
 __device__ __forceinline__ bool rect_contains(const Rect& r, int x, int y) { return r.sx <= x && r.ex >= x && r.sy <= y && r.ey >= y; }
 
@@ -57,59 +75,76 @@ __device__ __forceinline__ uint32_t cell_byte(const Params& P, uint32_t s) {
     return 1u;
 }
 
-// The 8 Moore neighbours of (cx, cy) in the reference's iterator order (geography/point.rs:59):
+// The 8 Moore neighbours of a cell in the reference's iterator order (geography/point.rs:59):
 // j: 0 (-1,-1) 1 (0,-1) 2 (1,-1) 3 (-1,0) 4 (1,0) 5 (-1,1) 6 (0,1) 7 (1,1)
 struct Hood {
     uint32_t lo, hi;  // grid bytes of neighbours 0..3 and 4..7
 };
-// 5x5 window of grid bytes centred on (cx, cy): row r (dy = r - 2) holds cells cx-2..cx+2 in bytes 0..4 of w[r].
-// Loaded as 10 independent aligned 32-bit loads so that one memory round trip serves both the walk (3x3 around the
-// base cell) and the exposure scan (3x3 around the proposed cell, at most one step away).  The grid allocation is
-// zero-padded by GRID_YPAD rows and GRID_XPAD bytes, so no bounds checks are needed.
+// 5x5 window of grid bytes centred on (cx, cy).  Row k (dy = k - 2): l[k] holds cells cx-2..cx+1, r[k] cells cx-1..cx+2.
 struct Window {
-    uint64_t w[5];
+    uint32_t l[5], r[5];
 };
 __device__ __forceinline__ Window load_window(const uint8_t* __restrict__ grid, uint32_t pitch, int cx, int cy) {
     const ptrdiff_t first = (ptrdiff_t)(cy - 2) * (ptrdiff_t)pitch + (cx - 2);  // offset of the window's top-left cell
-    const ptrdiff_t aligned = first & ~(ptrdiff_t)3;                            // grid base and pitch are multiples of 4
-    const uint32_t sh = (uint32_t)(first & 3) * 8u;
-    const uint32_t* p = reinterpret_cast<const uint32_t*>(grid + aligned);
+    const uint32_t sh = (uint32_t)(first & 3) * 8u;                             // grid base and pitch are multiples of 4
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(grid + (first & ~(ptrdiff_t)3));
     const uint32_t stride = pitch >> 2;
     uint32_t a[5], b[5];
 #pragma unroll
-    for (int r = 0; r < 5; ++r) {
-        a[r] = __ldg(p + (size_t)r * stride);
-        b[r] = __ldg(p + (size_t)r * stride + 1);
+    for (int k = 0; k < 5; ++k) {
+        a[k] = __ldg(p + (size_t)k * stride);
+        b[k] = __ldg(p + (size_t)k * stride + 1);
     }
     Window win;
 #pragma unroll
-    for (int r = 0; r < 5; ++r) win.w[r] = (((uint64_t)b[r] << 32) | a[r]) >> sh;
+    for (int k = 0; k < 5; ++k) {
+        win.l[k] = __funnelshift_r(a[k], b[k], sh);
+        win.r[k] = __funnelshift_rc(a[k], b[k], sh + 8u);
+    }
     return win;
 }
+// the 3x3 neighbourhood of the window's centre cell
+__device__ __forceinline__ Hood hood_centre(const Window& w) {
+    Hood h;
+    h.lo = (w.r[1] & 0x00FFFFFFu) | (w.r[2] << 24);
+    h.hi = ((w.r[2] >> 16) & 0xFFu) | (w.r[3] << 8);
+    return h;
+}
 // the 3x3 neighbourhood of the cell at offset (dx, dy) from the window centre, dx, dy in {-1, 0, 1}
-__device__ __forceinline__ Hood hood_at(const Window& win, int dx, int dy) {
-    const uint64_t r0 = dy < 0 ? win.w[0] : dy == 0 ? win.w[1] : win.w[2];
-    const uint64_t r1 = dy < 0 ? win.w[1] : dy == 0 ? win.w[2] : win.w[3];
-    const uint64_t r2 = dy < 0 ? win.w[2] : dy == 0 ? win.w[3] : win.w[4];
-    const uint32_t sh = (uint32_t)(dx + 1) * 8u;
-    const uint32_t top = (uint32_t)(r0 >> sh), mid = (uint32_t)(r1 >> sh), bot = (uint32_t)(r2 >> sh);
+__device__ __forceinline__ Hood hood_at(const Window& w, int dx, int dy) {
+    uint32_t t0 = dx < 0 ? w.l[0] : w.r[0], t1 = dx < 0 ? w.l[1] : w.r[1], t2 = dx < 0 ? w.l[2] : w.r[2];
+    const uint32_t t3 = dx < 0 ? w.l[3] : w.r[3], t4 = dx < 0 ? w.l[4] : w.r[4];
+    if (dy == 0) { t0 = t1; t1 = t2; t2 = t3; }
+    else if (dy > 0) { t0 = t2; t1 = t3; t2 = t4; }
+    const uint32_t sh = dx > 0 ? 8u : 0u;
+    const uint32_t top = t0 >> sh, mid = t1 >> sh, bot = t2 >> sh;
     Hood h;
     h.lo = (top & 0x00FFFFFFu) | (mid << 24);
     h.hi = ((mid >> 16) & 0xFFu) | (bot << 8);
     return h;
 }
-// per-byte predicate words (0xFF / 0x00 per byte) -> 8-bit neighbour mask
-__device__ __forceinline__ uint32_t mask_of(uint32_t lo_pred, uint32_t hi_pred) {
-    const uint32_t a = ((lo_pred & 0x08040201u) * 0x01010101u) >> 24;
-    const uint32_t b = ((hi_pred & 0x08040201u) * 0x01010101u) >> 24;
-    return a | (b << 4);
+// one bit per byte (the 0x01 position of each byte of `bits`) -> 4-bit mask
+__device__ __forceinline__ uint32_t gather4(uint32_t bits) { return ((bits & 0x01010101u) * 0x01020408u) >> 24; }
+// bit j set: neighbour j's cell is vacant (occupancy bits 0-1 clear; claim bits ignored)
+__device__ __forceinline__ uint32_t vacant_mask(const Hood& h) {
+    return gather4(~(h.lo | (h.lo >> 1))) | (gather4(~(h.hi | (h.hi >> 1))) << 4);
 }
+// bit j set: neighbour j holds an infected, not hospitalized agent with a non-zero rate class (occupancy value 2 or 3)
+__device__ __forceinline__ uint32_t infectious_mask(const Hood& h) { return gather4(h.lo >> 1) | (gather4(h.hi >> 1) << 4); }
+
 // Area::get_neighbors_of(c).filter(is_point_in_grid): which neighbours of (cx, cy) lie inside rectangle r and the grid
 // (geography/area.rs:56-58, allocation_map.rs:156-159).  (cx, cy) itself need not be inside r.
 __device__ __forceinline__ uint32_t valid_mask(const Rect& r, int G, int cx, int cy) {
     const int ex = min(r.ex, G - 1), ey = min(r.ey, G - 1);  // r.sx, r.sy >= 0 always
     const uint32_t cl = (cx - 1 >= r.sx) & (cx - 1 <= ex), cc = (cx >= r.sx) & (cx <= ex), cr = (cx + 1 >= r.sx) & (cx + 1 <= ex);
     const uint32_t ru = (cy - 1 >= r.sy) & (cy - 1 <= ey), rc = (cy >= r.sy) & (cy <= ey), rd = (cy + 1 >= r.sy) & (cy + 1 <= ey);
+    const uint32_t cols = cl | (cc << 1) | (cr << 2);
+    return (cols & (0u - ru)) | (((cl | (cr << 1)) & (0u - rc)) << 3) | ((cols & (0u - rd)) << 5);
+}
+// the same when (cx, cy) is known to lie inside r
+__device__ __forceinline__ uint32_t valid_mask_inside(const Rect& r, int G, int cx, int cy) {
+    const uint32_t cl = cx > r.sx, cc = cx < G, cr = cx < min(r.ex, G - 1);
+    const uint32_t ru = cy > r.sy, rc = cy < G, rd = cy < min(r.ey, G - 1);
     const uint32_t cols = cl | (cc << 1) | (cr << 2);
     return (cols & (0u - ru)) | (((cl | (cr << 1)) & (0u - rc)) << 3) | ((cols & (0u - rd)) << 5);
 }
@@ -127,12 +162,26 @@ __device__ __forceinline__ int select_bit(uint32_t m, uint32_t idx) {
 __device__ __forceinline__ int hood_dx(int j) { return (int)((0x9224u >> (2 * j)) & 3u) - 1; }  // {-1,0,1,-1,1,-1,0,1}
 __device__ __forceinline__ int hood_dy(int j) { return (int)((0xA940u >> (2 * j)) & 3u) - 1; }  // {-1,-1,-1,0,0,1,1,1}
 
+// Philox4x32-10 with the key schedule taken from Params (constant bank operands)
+__device__ __forceinline__ U4 philox_rk(const Params& P, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        c0 = hi1 ^ c1 ^ P.rk[r][0];
+        c2 = hi0 ^ c3 ^ P.rk[r][1];
+        c1 = lo1;
+        c3 = lo0;
+    }
+    return U4{c0, c1, c2, c3};
+}
+
 template <bool INJECT>
 struct Draws {
-    uint64_t seed;
+    const Params& P;
     uint32_t agent, hour;
     const uint64_t* row;
-    __device__ __forceinline__ U4 block(uint32_t b) const { return philox4x32_10(agent, hour, b, DOM_STEP, (uint32_t)seed, (uint32_t)(seed >> 32)); }
+    __device__ __forceinline__ U4 block(uint32_t b) const { return philox_rk(P, agent, hour, b, DOM_STEP); }
     // block 0: PICK, FACTOR, A
     __device__ __forceinline__ void common(uint32_t& pick, uint32_t& factor, uint64_t& a) const {
         if (INJECT) { pick = (uint32_t)row[SLOT_PICK]; factor = (uint32_t)row[SLOT_FACTOR]; a = row[SLOT_A]; return; }
@@ -144,8 +193,8 @@ struct Draws {
         uint32_t dx, dy;
         if (INJECT) { dx = (uint32_t)row[SLOT_PX]; dy = (uint32_t)row[SLOT_PY]; }
         else { const U4 o = block(1); dx = o.x; dy = o.y; }
-        px = r.sx + (int)mulhi32(dx, (uint32_t)(r.ex - r.sx + 1));
-        py = r.sy + (int)mulhi32(dy, (uint32_t)(r.ey - r.sy + 1));
+        px = r.sx + (int)__umulhi(dx, (uint32_t)(r.ex - r.sx + 1));
+        py = r.sy + (int)__umulhi(dy, (uint32_t)(r.ey - r.sy + 1));
     }
     __device__ __forceinline__ uint64_t expose(int j) const {
         if (INJECT) return row[SLOT_EXPOSE0 + j];
@@ -174,222 +223,235 @@ __device__ __forceinline__ uint32_t count_category(uint32_t s) {
 }
 
 __global__ void __launch_bounds__(256) k_hospital_scan(Params P, const uint8_t* __restrict__ grid, uint32_t* __restrict__ hosp_first) {
-    const Rect h = P.hospital[P.hospital_gen];
+    const Rect h = P.hospital();
     const uint32_t w = (uint32_t)(h.ex - h.sx + 1), nh = (uint32_t)(h.ey - h.sy + 1);
     const uint64_t total = (uint64_t)w * nh;
     for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < total; r += (uint64_t)gridDim.x * blockDim.x) {
         if (r >= *(volatile uint32_t*)hosp_first) return;  // ranks only grow along the stride: nothing better ahead
         const uint32_t x = (uint32_t)h.sx + (uint32_t)(r % w), y = (uint32_t)h.sy + (uint32_t)(r / w);
-        if (grid[(size_t)y * P.pitch + x] == 0) { atomicMin(hosp_first, (uint32_t)r); return; }
+        if ((grid[(size_t)y * P.pitch + x] & CELL_OCC_MASK) == 0) { atomicMin(hosp_first, (uint32_t)r); return; }
     }
 }
 
 template <int KIND, bool INJECT>
-__global__ void __launch_bounds__(256) k_hour(Params P, DevPtrs D, uint32_t hour_offset) {
+__global__ void __launch_bounds__(256, KIND == KIND_MOVE ? 5 : 4) k_hour(Params P, DevPtrs D, uint32_t hour_offset, uint32_t h) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n) return;
+    // one round trip: the agent's state words (and the uniform clock word)
+    const uint32_t s0 = ld_early_rw(D.st + i);
+    const uint32_t c0 = ld_early_rw(D.cell + i);
+    const uint32_t hm = ld_early(D.home + i);
+    const uint32_t wk = KIND == KIND_MOVE ? ld_early(D.work + i) : 0u;
     const uint32_t hour = D.clock->hour_base + hour_offset;
-    uint32_t cat = 6;
-    if (i < P.n) {
-        const uint32_t s0 = D.st[i];
-        const uint32_t c0 = D.cell[i];
-        const uint32_t hm = D.home[i];
-        const uint32_t wk = KIND == KIND_MOVE ? D.work[i] : 0u;  // all four loads issued together: one memory round trip
-        const int x = (int)(c0 & CELL_XMASK), y = (int)(c0 >> CELL_BITS);
-        const uint8_t* __restrict__ grid = D.grid;
-        uint32_t s = s0;
-        int tx = x, ty = y;
-        const Draws<INJECT> dr{P.seed, i, hour, INJECT ? D.draws + (size_t)i * 16 : nullptr};
-        const uint32_t ws = (s0 >> ST_WS_SHIFT) & 3u;
-        uint32_t state = s0 & ST_STATE_MASK, sev = (s0 >> ST_SEV_SHIFT) & 3u, day = s0 >> ST_DAY_SHIFT;
-        const Rect home = origin_rect(hm, 1);
+    const int x = (int)(c0 & CELL_XMASK), y = (int)(c0 >> CELL_BITS);
+    const uint8_t* __restrict__ grid = D.grid;
+    uint32_t s = s0;
+    int tx = x, ty = y;
+    const Draws<INJECT> dr{P, i, hour, INJECT ? D.draws + (size_t)i * 16 : nullptr};
+    const uint32_t ws = (s0 >> ST_WS_SHIFT) & 3u;
+    uint32_t state = s0 & ST_STATE_MASK, sev = (s0 >> ST_SEV_SHIFT) & 3u, day = s0 >> ST_DAY_SHIFT;
+    const Rect home = origin_rect(hm, 1);
 
-        if (KIND == KIND_START) {
-            // ROUTINE_START_TIME: increment_infection_day + hospitalize (citizen/mod.rs:240-243, :351-365)
-            if (state == ST_I) {
-                day = min(day + 1u, ST_DAY_MAX);
-                const int imm = (int)((s0 >> ST_IMM_SHIFT) & 7u) - 2;
-                if (!(s0 & ST_HOSP) && sev == SEV_SEVERE && ((P.hospitalize_mask >> rate_class(P, (uint32_t)((int)day + imm))) & 1u)) {
-                    const uint32_t first = *D.hosp_first;
-                    if (first != HOSP_NONE) {  // goto_hospital: every admitted agent targets the same first vacant cell
-                        const Rect hr = P.hospital[P.hospital_gen];
-                        const uint32_t w = (uint32_t)(hr.ex - hr.sx + 1);
-                        tx = hr.sx + (int)(first % w); ty = hr.sy + (int)(first / w);
-                        s |= ST_HOSP;
-                    } else {  // hospital full: try a random point of the own house
-                        int px, py;
-                        dr.point(home, px, py);
-                        if (grid[(size_t)py * P.pitch + px] == 0) { tx = px; ty = py; }
-                    }
+    if (KIND == KIND_START) {
+        // ROUTINE_START_TIME: increment_infection_day + hospitalize (citizen/mod.rs:240-243, :351-365)
+        if (state == ST_I) {
+            day = min(day + 1u, ST_DAY_MAX);
+            const int imm = (int)((s0 >> ST_IMM_SHIFT) & 7u) - 2;
+            if (!(s0 & ST_HOSP) && sev == SEV_SEVERE && ((P.hospitalize_mask >> rate_class(P, (uint32_t)((int)day + imm))) & 1u)) {
+                const uint32_t first = *D.hosp_first;
+                if (first != HOSP_NONE) {  // goto_hospital: every admitted agent targets the same first vacant cell
+                    const Rect hr = P.hospital();
+                    const uint32_t w = (uint32_t)(hr.ex - hr.sx + 1);
+                    tx = hr.sx + (int)(first % w); ty = hr.sy + (int)(first / w);
+                    s |= ST_HOSP;
+                } else {  // hospital full: try a random point of the own house
+                    int px, py;
+                    dr.point(home, px, py);
+                    if ((grid[(size_t)py * P.pitch + px] & CELL_OCC_MASK) == 0) { tx = px; ty = py; }
                 }
             }
-        } else if (KIND == KIND_END) {
-            // ROUTINE_END_TIME: Citizen::deceased + on_routine_end (citizen/mod.rs:397-413, default_disease_handler.rs:88-103)
-            if (state == ST_I) {
-                if ((sev == SEV_ASYM && day == 9u) || (sev == SEV_MILD && day == 12u)) state = ST_R;
-                else if (sev == SEV_SEVERE && day == P.last_day) {
-                    uint32_t pick, factor; uint64_t a;
-                    dr.common(pick, factor, a);
-                    state = bernoulli(a, P.thr_death) ? ST_D : ST_R;
-                }
+        }
+    } else if (KIND == KIND_END) {
+        // ROUTINE_END_TIME: Citizen::deceased + on_routine_end (citizen/mod.rs:397-413, default_disease_handler.rs:88-103)
+        if (state == ST_I) {
+            if ((sev == SEV_ASYM && day == 9u) || (sev == SEV_MILD && day == 12u)) state = ST_R;
+            else if (sev == SEV_SEVERE && day == P.last_day) {
+                uint32_t pick, factor; uint64_t a;
+                dr.common(pick, factor, a);
+                state = bernoulli(a, P.thr_death) ? ST_D : ST_R;
             }
-            if (state == ST_R) {  // every recovered agent, every day
-                int px, py;
-                dr.point(home, px, py);
-                if (grid[(size_t)py * P.pitch + px] == 0) { tx = px; ty = py; }
+        }
+        if (state == ST_R) {  // every recovered agent, every day
+            int px, py;
+            dr.point(home, px, py);
+            if ((grid[(size_t)py * P.pitch + px] & CELL_OCC_MASK) == 0) { tx = px; ty = py; }
+        }
+        if (state == ST_R || state == ST_D) { s &= ~ST_HOSP; sev = 0; day = 0; }
+    } else {
+        // perform_movements (citizen/mod.rs:257-349); h in 7..22 here (sleep hours use k_sleep)
+        const uint32_t kind0 = (s0 >> ST_AREA_SHIFT) & 7u;
+        const bool symptomatic = state == ST_I && sev >= SEV_MILD;
+        const bool can_move = !(symptomatic || (s0 & (ST_HOSP | ST_ISO)) || state == ST_D);  // citizen/mod.rs:452-454
+        const bool pre = state == ST_I && sev == SEV_PRE;
+        // at_hour of Exposed / Pre: requested now, consumed after the window arrives
+        uint32_t t0v = 0;
+        if (state == ST_E || pre) t0v = ld_early_rw(D.t0 + i);
+        const Rect workr = ws == WS_NA ? home : origin_rect(wk, 9);
+        auto rect_of = [&](uint32_t kind) -> Rect {
+            Rect r = kind == AK_WORK ? workr : home;
+            if (kind >= AK_TRANSPORT) r = P.zone[kind - AK_TRANSPORT];
+            return r;
+        };
+        // the hour's rule -> (mode, rectangle R, new current_area kind).  goto_area for a non-working agent is
+        // move_agent_from in the (old) current_area (citizen/mod.rs:386-394), i.e. MODE_WALK.
+        Rect R = rect_of(kind0);
+        uint32_t kind = kind0;
+        int mode = MODE_WALK;
+        bool dynamics = true, override_movement = false;
+        if (ws == WS_NA) {
+            if (h == 8) kind = AK_HOUSING;
+            else if (h == 12) kind = AK_HOME;
+        } else if (ws != WS_STAFF) {  // Normal | Essential
+            if (h == 7 || h == 17) {
+                if (s0 & ST_PT) { mode = MODE_GOTO; R = P.transport(); kind = AK_TRANSPORT; }
+            } else if (h == 8) { mode = MODE_GOTO; R = workr; kind = AK_WORK; }
+            else if (h == 16) {
+                mode = MODE_GOTO; R = home; kind = AK_HOME;
+                override_movement = symptomatic && rect_contains(workr, x, y);  // citizen/mod.rs:373-381
             }
-            if (state == ST_R || state == ST_D) { s &= ~ST_HOSP; sev = 0; day = 0; }
-        } else {
-            // perform_movements (citizen/mod.rs:257-349); h in 7..22 here (sleep hours use k_sleep)
-            const uint32_t h = hour % 24u;
-            const uint32_t kind0 = (s0 >> ST_AREA_SHIFT) & 7u;
-            const bool symptomatic = state == ST_I && sev >= SEV_MILD;
-            const bool can_move = !(symptomatic || (s0 & (ST_HOSP | ST_ISO)) || state == ST_D);  // citizen/mod.rs:452-454
-            const Rect workr = ws == WS_NA ? home : origin_rect(wk, 9);
-            auto rect_of = [&](uint32_t kind) -> Rect {
-                switch (kind) {
-                    case AK_HOME: return home;
-                    case AK_WORK: return workr;
-                    case AK_TRANSPORT: return P.transport;
-                    case AK_HOUSING: return P.housing;
-                    case AK_HOSPITAL0: return P.hospital[0];
-                    default: return P.hospital[1];
+        } else {  // HospitalStaff { work_start_at } (0.14 % of agents)
+            const uint32_t wsa = D.wsa[i];
+            const uint32_t since = hour >= wsa ? hour - wsa : 0u;  // saturating_sub
+            const uint32_t hosp_kind = P.hospital_gen ? AK_HOSPITAL1 : AK_HOSPITAL0;
+            if (since == 24u * 14u) { s |= ST_WQ; dynamics = false; mode = MODE_STAY; }
+            else if (since == 24u * 14u * 2u) {
+                mode = MODE_GOTO; R = home; kind = AK_HOME;
+                D.wsa[i] = hour + 24u * 14u;
+                dynamics = false;
+            } else if (h == 8) {
+                mode = MODE_STAY;
+                if (kind0 != hosp_kind && wsa <= hour) {
+                    mode = MODE_GOTO; R = P.hospital(); kind = hosp_kind;
+                    D.wsa[i] = hour;
                 }
-            };
-            // the hour's rule -> (mode, rectangle R, new current_area kind).  goto_area for a non-working agent is
-            // move_agent_from in the (old) current_area (citizen/mod.rs:386-394), i.e. MODE_WALK.
-            Rect R = rect_of(kind0);
-            uint32_t kind = kind0;
-            int mode = MODE_WALK;
-            bool dynamics = true, override_movement = false;
-            if (ws == WS_NA) {
-                if (h == 8) kind = AK_HOUSING;
-                else if (h == 12) kind = AK_HOME;
-            } else if (ws != WS_STAFF) {  // Normal | Essential
-                if (h == 7 || h == 17) {
-                    if (s0 & ST_PT) { mode = MODE_GOTO; R = P.transport; kind = AK_TRANSPORT; }
-                } else if (h == 8) { mode = MODE_GOTO; R = workr; kind = AK_WORK; }
-                else if (h == 16) {
-                    mode = MODE_GOTO; R = home; kind = AK_HOME;
-                    override_movement = symptomatic && rect_contains(workr, x, y);  // citizen/mod.rs:373-381
-                }
-            } else {  // HospitalStaff { work_start_at } (0.14 % of agents)
-                const uint32_t wsa = D.wsa[i];
-                const uint32_t since = hour >= wsa ? hour - wsa : 0u;  // saturating_sub
-                const uint32_t hosp_kind = P.hospital_gen ? AK_HOSPITAL1 : AK_HOSPITAL0;
-                if (since == 24u * 14u) { s |= ST_WQ; dynamics = false; mode = MODE_STAY; }
-                else if (since == 24u * 14u * 2u) {
-                    mode = MODE_GOTO; R = home; kind = AK_HOME;
-                    D.wsa[i] = hour + 24u * 14u;
-                    dynamics = false;
-                } else if (h == 8) {
-                    mode = MODE_STAY;
-                    if (kind0 != hosp_kind && wsa <= hour) {
-                        mode = MODE_GOTO; R = P.hospital[P.hospital_gen]; kind = hosp_kind;
-                        D.wsa[i] = hour;
-                    }
-                    s &= ~ST_WQ;
-                } else if (h == 16) { s |= ST_WQ; mode = MODE_STAY; }
-                else if (s0 & ST_WQ) mode = MODE_STAY;
-            }
-            if (!(can_move || override_movement)) mode = MODE_STAY;
-            s = (s & ~ST_AREA_MASK) | (kind << ST_AREA_SHIFT);
+                s &= ~ST_WQ;
+            } else if (h == 16) { s |= ST_WQ; mode = MODE_STAY; }
+            else if (s0 & ST_WQ) mode = MODE_STAY;
+        }
+        if (!(can_move || override_movement)) mode = MODE_STAY;
+        s = (s & ~ST_AREA_MASK) | (kind << ST_AREA_SHIFT);
 
-            const bool in_area = rect_contains(R, x, y);
-            const bool need_point = mode == MODE_GOTO || (mode == MODE_WALK && !in_area);
-            const bool pre = state == ST_I && sev == SEV_PRE;
-            uint32_t pick = 0, factor = 0;
-            uint64_t a = 0;
-            if (mode == MODE_WALK || (dynamics && (state == ST_E || pre))) dr.common(pick, factor, a);
-            int bx = x, by = y;
-            if (need_point) dr.point(R, bx, by);
-            const bool scan = dynamics && state == ST_S && !(s & (ST_WQ | ST_VACC));
-            int ddx = 0, ddy = 0;  // proposed cell relative to the window centre (bx, by)
-            Window win;
-            if (mode != MODE_STAY || scan) win = load_window(grid, P.pitch, bx, by);
-            if (mode == MODE_GOTO) {
-                if ((uint8_t)(win.w[2] >> 16) == 0) { tx = bx; ty = by; }  // target.get_random_point vacant -> go (citizen/mod.rs:387-392)
-            } else if (mode == MODE_WALK) {  // Citizen::move_agent_from (citizen/mod.rs:415-432)
-                const Hood hd = hood_at(win, 0, 0);
-                const uint32_t vacant = mask_of(__vcmpeq4(hd.lo, 0u), __vcmpeq4(hd.hi, 0u));
-                const uint32_t cand = vacant & valid_mask(R, P.grid_size, bx, by);
-                if (cand) {
-                    const int j = select_bit(cand, mulhi32(pick, (uint32_t)__popc(cand)));
-                    ddx = hood_dx(j); ddy = hood_dy(j);
-                    tx = bx + ddx; ty = by + ddy;
-                }
+        const bool in_area = rect_contains(R, x, y);
+        const bool need_point = mode == MODE_GOTO || (mode == MODE_WALK && !in_area);
+        const bool scan = dynamics && state == ST_S && !(s & (ST_WQ | ST_VACC));
+        int bx = x, by = y;
+        if (need_point) dr.point(R, bx, by);
+        // second round trip: the 5x5 window around the base cell
+        Window win;
+        if (mode != MODE_STAY || scan) win = load_window(grid, P.pitch, bx, by);
+        uint32_t pick = 0, factor = 0;
+        uint64_t a = 0;
+        if (mode == MODE_WALK || (dynamics && (state == ST_E || pre))) dr.common(pick, factor, a);
+        int ddx = 0, ddy = 0;  // proposed cell relative to the window centre (bx, by)
+        if (mode == MODE_GOTO) {
+            if (((win.r[2] >> 8) & CELL_OCC_MASK) == 0) { tx = bx; ty = by; }  // target.get_random_point vacant -> go (citizen/mod.rs:387-392)
+        } else if (mode == MODE_WALK) {  // Citizen::move_agent_from (citizen/mod.rs:415-432)
+            const uint32_t cand = vacant_mask(hood_centre(win)) & valid_mask_inside(R, P.grid_size, bx, by);
+            if (cand) {
+                const int j = select_bit(cand, __umulhi(pick, (uint32_t)__popc(cand)));
+                ddx = hood_dx(j); ddy = hood_dy(j);
+                tx = bx + ddx; ty = by + ddy;
             }
-            if (dynamics) {
-                // DiseaseStateMachine::next at the proposed cell (disease_state_machine.rs:53-70)
-                if (state == ST_S) {
-                    if (scan) {  // on_susceptible, default_disease_handler.rs:64-86
-                        // the proposed cell is the window centre + (ddx, ddy), or the agent's own cell when the move
-                        // was not possible: a relocated walker / a goto that found its point occupied stays at (x, y),
-                        // which is outside the window -> rare second load
-                        Hood hd;
-                        if (tx == bx + ddx && ty == by + ddy) hd = hood_at(win, ddx, ddy);
-                        else hd = hood_at(load_window(grid, P.pitch, tx, ty), 0, 0);
-                        uint32_t inf = mask_of(__vcmpgeu4(hd.lo, 0x02020202u), __vcmpgeu4(hd.hi, 0x02020202u));
-                        // neighbours are clipped to the NEW current_area: R is its rectangle unless a non-working agent's
-                        // area changed this hour (h = 8, 12), where R is still the old one
-                        if (inf) inf &= valid_mask(kind == kind0 ? R : rect_of(kind), P.grid_size, tx, ty);
-                        while (inf) {
-                            const int j = __ffs(inf) - 1;
-                            inf &= inf - 1u;
-                            const uint32_t b = ((j < 4 ? hd.lo : hd.hi) >> (8 * (j & 3))) & 0xFFu;
-                            if (bernoulli(dr.expose(j), P.thr_rate[b - 1u])) {
-                                state = ST_E;
-                                D.t0[i] = hour;
-                                break;
-                            }
+        }
+        if (dynamics) {
+            // DiseaseStateMachine::next at the proposed cell (disease_state_machine.rs:53-70)
+            if (state == ST_S) {
+                if (scan) {  // on_susceptible, default_disease_handler.rs:64-86
+                    // the proposed cell is the window centre + (ddx, ddy), or the agent's own cell when the move was
+                    // not possible: a relocated walker / a goto that found its point occupied stays at (x, y), which
+                    // is outside the window -> second load (hours 7, 8, 16, 17 mostly)
+                    Hood hd;
+                    if (tx == bx + ddx && ty == by + ddy) hd = hood_at(win, ddx, ddy);
+                    else hd = hood_centre(load_window(grid, P.pitch, tx, ty));
+                    uint32_t inf = infectious_mask(hd);
+                    // neighbours are clipped to the NEW current_area: R is its rectangle unless a non-working agent's
+                    // area changed this hour (h = 8, 12), where R is still the old one
+                    if (inf) inf &= valid_mask(kind == kind0 ? R : rect_of(kind), P.grid_size, tx, ty);
+                    while (inf) {
+                        const int j = __ffs(inf) - 1;
+                        inf &= inf - 1u;
+                        const uint32_t b = ((j < 4 ? hd.lo : hd.hi) >> (8 * (j & 3))) & CELL_OCC_MASK;
+                        if (bernoulli(dr.expose(j), P.thr_rate[b - 1u])) {
+                            state = ST_E;
+                            D.t0[i] = hour;
+                            break;
                         }
                     }
-                } else if (state == ST_E) {  // on_exposed, :52-62
-                    const int f = (int)mulhi32(factor, 3u) - 1;
-                    if (hour - D.t0[i] >= (uint32_t)((int)P.exposed_duration + f)) {
-                        const bool symptoms = bernoulli(a, P.thr_symptomatic);
-                        state = ST_I; day = 0;
-                        sev = symptoms ? SEV_PRE : SEV_ASYM;
-                        if (symptoms) D.t0[i] = hour;
-                    }
-                } else if (pre) {  // on_infected, :41-50
-                    if (hour - D.t0[i] >= P.pre_symptomatic_duration) sev = bernoulli(a, P.thr_severe) ? SEV_SEVERE : SEV_MILD;
                 }
+            } else if (state == ST_E) {  // on_exposed, :52-62
+                const int f = (int)__umulhi(factor, 3u) - 1;
+                if (hour - t0v >= (uint32_t)((int)P.exposed_duration + f)) {
+                    const bool symptoms = bernoulli(a, P.thr_symptomatic);
+                    state = ST_I; day = 0;
+                    sev = symptoms ? SEV_PRE : SEV_ASYM;
+                    if (symptoms) D.t0[i] = hour;
+                }
+            } else if (pre) {  // on_infected, :41-50
+                if (hour - t0v >= P.pre_symptomatic_duration) sev = bernoulli(a, P.thr_severe) ? SEV_SEVERE : SEV_MILD;
             }
         }
-        // re-pack
-        s = (s & ~(ST_STATE_MASK | (3u << ST_SEV_SHIFT) | (ST_DAY_MAX << ST_DAY_SHIFT))) | state | (sev << ST_SEV_SHIFT) | (day << ST_DAY_SHIFT);
-        if (s != s0) D.st[i] = s;
-        const uint32_t b_old = cell_byte(P, s0), b_new = cell_byte(P, s);
-        uint32_t prop = 0;
-        if (b_new != b_old) prop |= PROP_DIRTY;
-        if (tx != x || ty != y) {
-            prop |= PROP_MOVE | ((uint32_t)ty << CELL_BITS) | (uint32_t)tx;
-            const uint32_t stamp = hour - D.clock->epoch_base + 1u;
-            const uint32_t id_mask = (1u << P.id_bits) - 1u;
-            atomicMax(&D.claim[(size_t)ty * P.pitch + (size_t)tx], (stamp << P.id_bits) | (id_mask - i));
-        }
-        if (prop) prop |= (b_new - 1u) << PROP_BYTE_SHIFT;
-        D.prop[i] = prop;
-        cat = count_category(s);
     }
-    block_count(cat, D.counts + (size_t)(hour - D.clock->ring_base) * 8);
+    // re-pack
+    s = (s & ~(ST_STATE_MASK | (3u << ST_SEV_SHIFT) | (ST_DAY_MAX << ST_DAY_SHIFT))) | state | (sev << ST_SEV_SHIFT) | (day << ST_DAY_SHIFT);
+    uint32_t prop = 0;
+    if (s != s0) {
+        D.st[i] = s;
+        // Counts::update_counts (counts.rs:126-140), incrementally: only an agent whose column changed touches the running
+        // totals (TOT_COPIES spread copies against same-address contention); k_commit snapshots them into the hour's row.
+        const uint32_t cat0 = count_category(s0), cat1 = count_category(s);
+        if (cat0 != cat1) {
+            uint32_t* t = D.tot + (blockIdx.x & (TOT_COPIES - 1u)) * 8u;
+            atomicAdd(t + cat1, 1u);
+            atomicSub(t + cat0, 1u);
+        }
+        if (cell_byte(P, s) != cell_byte(P, s0)) prop |= PROP_DIRTY;
+    }
+    if (tx != x || ty != y) {
+        prop |= PROP_MOVE | ((uint32_t)ty << CELL_BITS) | (uint32_t)tx;
+        const uint32_t stamp = hour - D.clock->epoch_base + 1u;
+        const uint32_t id_mask = (1u << P.id_bits) - 1u;
+        atomicMax(&D.claim[(size_t)ty * P.pitch + (size_t)tx], (stamp << P.id_bits) | (id_mask - i));
+    }
+    if (prop) prop |= (cell_byte(P, s) - 1u) << PROP_BYTE_SHIFT;
+    D.prop[i] = prop;
 }
 
 __global__ void __launch_bounds__(256) k_commit(Params P, DevPtrs D, uint32_t hour_offset) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t hour = D.clock->hour_base + hour_offset;
+    if (blockIdx.x == 0 && threadIdx.x < 32) {
+        // the hour's Counts row = sum of the running totals' copies (all k_hour blocks of this hour have finished)
+#pragma unroll
+        for (uint32_t c = 0; c < 6; ++c) {
+            uint32_t v = threadIdx.x < TOT_COPIES ? D.tot[threadIdx.x * 8u + c] : 0u;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+            if (threadIdx.x == 0) D.counts[(size_t)(hour - D.clock->ring_base) * 8 + c] = v;
+        }
+    }
     if (i >= P.n) return;
     const uint32_t prop = D.prop[i];
     const uint32_t c0 = D.cell[i];  // issued with the prop load: one memory round trip
-    const uint32_t hour = D.clock->hour_base + hour_offset;
     if (prop == 0) return;
     const uint32_t byte = (prop >> PROP_BYTE_SHIFT) + 1u;
-    size_t at = (size_t)(c0 >> CELL_BITS) * P.pitch + (c0 & CELL_XMASK);
+    const size_t at = (size_t)(c0 >> CELL_BITS) * P.pitch + (c0 & CELL_XMASK);
     if (prop & PROP_MOVE) {
-        const uint32_t stamp = hour - D.clock->epoch_base + 1u;
-        const uint32_t id_mask = (1u << P.id_bits) - 1u;
         const uint32_t tc = prop & PROP_CELL_MASK;
         const size_t tat = (size_t)(tc >> CELL_BITS) * P.pitch + (tc & CELL_XMASK);
-        if (D.claim[tat] == ((stamp << P.id_bits) | (id_mask - i))) {  // lowest id among claimants: upcoming.entry(new).or_insert
+        const uint32_t stamp = hour - D.clock->epoch_base + 1u;
+        const uint32_t id_mask = (1u << P.id_bits) - 1u;
+        const bool win = D.claim[tat] == ((stamp << P.id_bits) | (id_mask - i));  // lowest id among claimants: upcoming.entry(new).or_insert
+        if (win) {
             D.grid[at] = 0;
             D.grid[tat] = (uint8_t)byte;
             D.cell[i] = tc;
@@ -416,6 +478,12 @@ __global__ void __launch_bounds__(256) k_sleep(Params P, DevPtrs D, uint32_t hou
 }
 
 __global__ void k_set_clock(Clock* clock, Clock value) { *clock = value; }
+
+// absolute recount into copy 0 of the running totals (the other copies must have been zeroed): create / reset / set_state
+__global__ void __launch_bounds__(256) k_recount(Params P, const uint32_t* __restrict__ st, uint32_t* __restrict__ tot) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    block_count(i < P.n ? count_category(st[i]) : 6u, tot);
+}
 
 __global__ void __launch_bounds__(256) k_lock(Params P, uint32_t* __restrict__ st) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -454,7 +522,7 @@ __global__ void __launch_bounds__(256) k_build_grid(Params P, const uint32_t* __
 static inline unsigned blocks_for(uint32_t n) { return (n + 255u) / 256u; }
 
 void launch_hospital_scan(const Params& P, const DevPtrs& D, cudaStream_t s) {
-    const Rect h = P.hospital[P.hospital_gen];
+    const Rect h = P.hospital();
     const uint64_t total = (uint64_t)(h.ex - h.sx + 1) * (uint64_t)(h.ey - h.sy + 1);
     unsigned blocks = (unsigned)((total + 255) / 256);
     if (blocks > 148u * 8u) blocks = 148u * 8u;
@@ -464,14 +532,15 @@ void launch_hospital_scan(const Params& P, const DevPtrs& D, cudaStream_t s) {
 template <bool INJECT>
 static void launch_hour_t(const Params& P, const DevPtrs& D, uint32_t hour_of_day, uint32_t hour_offset, cudaStream_t s) {
     const unsigned b = blocks_for(P.n);
-    if (hour_of_day == 0) k_hour<KIND_START, INJECT><<<b, 256, 0, s>>>(P, D, hour_offset);
-    else if (hour_of_day == 23) k_hour<KIND_END, INJECT><<<b, 256, 0, s>>>(P, D, hour_offset);
-    else k_hour<KIND_MOVE, INJECT><<<b, 256, 0, s>>>(P, D, hour_offset);
+    if (hour_of_day == 0) k_hour<KIND_START, INJECT><<<b, 256, 0, s>>>(P, D, hour_offset, hour_of_day);
+    else if (hour_of_day == 23) k_hour<KIND_END, INJECT><<<b, 256, 0, s>>>(P, D, hour_offset, hour_of_day);
+    else k_hour<KIND_MOVE, INJECT><<<b, 256, 0, s>>>(P, D, hour_offset, hour_of_day);
 }
 void launch_hour(const Params& P, const DevPtrs& D, uint32_t hour_of_day, uint32_t hour_offset, bool inject, cudaStream_t s) {
     if (inject) launch_hour_t<true>(P, D, hour_of_day, hour_offset, s);
     else launch_hour_t<false>(P, D, hour_of_day, hour_offset, s);
 }
+void launch_recount(const Params& P, const DevPtrs& D, cudaStream_t s) { k_recount<<<blocks_for(P.n), 256, 0, s>>>(P, D.st, D.tot); }
 void launch_set_clock(Clock* clock, const Clock& value, cudaStream_t s) { k_set_clock<<<1, 1, 0, s>>>(clock, value); }
 void launch_commit(const Params& P, const DevPtrs& D, uint32_t hour_offset, cudaStream_t s) { k_commit<<<blocks_for(P.n), 256, 0, s>>>(P, D, hour_offset); }
 void launch_sleep(const Params& P, const DevPtrs& D, uint32_t hour_offset, cudaStream_t s) { k_sleep<<<blocks_for(P.n), 256, 0, s>>>(P, D, hour_offset); }

@@ -7,6 +7,7 @@
 namespace epi {
 void launch_hospital_scan(const Params& P, const DevPtrs& D, cudaStream_t s);
 void launch_hour(const Params& P, const DevPtrs& D, uint32_t hour_of_day, uint32_t hour_offset, bool inject, cudaStream_t s);
+void launch_recount(const Params& P, const DevPtrs& D, cudaStream_t s);
 void launch_set_clock(Clock* clock, const Clock& value, cudaStream_t s);
 void launch_commit(const Params& P, const DevPtrs& D, uint32_t hour_offset, cudaStream_t s);
 void launch_sleep(const Params& P, const DevPtrs& D, uint32_t hour_offset, cudaStream_t s);

@@ -18,6 +18,10 @@
 //   claim[cells] u32  (stamp << id_bits) | (id_mask - agent id), atomicMax: lowest agent id wins the cell this hour
 #pragma once
 #include <stdint.h>
+#if !defined(__CUDACC__)
+#define __host__
+#define __device__
+#endif
 
 namespace epi {
 
@@ -53,7 +57,9 @@ constexpr uint32_t PROP_MOVE = 1u << 28;   // agent wants to move to bits 0..27
 constexpr uint32_t PROP_DIRTY = 1u << 29;  // the agent's grid byte changed
 constexpr int PROP_BYTE_SHIFT = 30;        // new grid byte - 1
 
+constexpr uint32_t CELL_OCC_MASK = 0x3u;
 constexpr uint32_t HOSP_NONE = 0xFFFFFFFFu;
+constexpr uint32_t TOT_COPIES = 32;  // power of two, <= 32
 constexpr uint32_t ORIGIN_MASK = (1u << 28) - 1;  // home / work words: packed origin in the low 28 bits
 constexpr uint32_t GRID_XPAD = 16;                // zero bytes before the start of row 0 in the grid allocation
 constexpr uint32_t GRID_YPAD = 3;                 // zero rows above row 0 and below the last row
@@ -68,9 +74,12 @@ struct Params {
     int grid_size;     // G: is_point_in_grid is 0 <= x,y < G (allocation_map.rs:156-159)
     uint32_t pitch;    // bytes per grid row
     uint32_t rows;
-    Rect housing, transport, work;  // geography/mod.rs:33-70
-    Rect hospital[2];               // [0] after Grid::resize_hospital, [1] after increase_hospital_size
-    int hospital_gen;               // which one is grid.hospital_area now
+    // the shared rectangles a current_area kind >= AK_TRANSPORT names: zone[kind - AK_TRANSPORT] =
+    // transport strip, housing strip (geography/mod.rs:33-70), hospital after Grid::resize_hospital, hospital after
+    // increase_hospital_size (grid.rs:233-261)
+    Rect zone[4];
+    Rect work;         // the work strip (offices live here)
+    int hospital_gen;  // which hospital rectangle is grid.hospital_area now: zone[2 + hospital_gen]
     int house_nx, office_nx;        // houses / offices per row (area_factory, geography/area.rs:95-117)
     // disease (common/src/disease/mod.rs:26-45)
     uint32_t regular_start, high_start, last_day;
@@ -80,7 +89,11 @@ struct Params {
     uint32_t hospitalize_mask;  // bit c set: rate class c satisfies Disease::is_to_be_hospitalized (disease/mod.rs:97-99)
     uint32_t id_bits;           // claim word: low id_bits = id_mask - agent
     uint64_t seed;
+    uint32_t rk[10][2];         // Philox round keys of `seed` (key schedule hoisted out of the kernels)
     int region;
+    __host__ __device__ const Rect& transport() const { return zone[0]; }
+    __host__ __device__ const Rect& housing() const { return zone[1]; }
+    __host__ __device__ const Rect& hospital() const { return zone[2 + hospital_gen]; }
 };
 
 struct Clock {           // device-resident so CUDA graphs can be replayed for any day
@@ -95,6 +108,7 @@ struct DevPtrs {
     uint8_t* grid;
     uint32_t* claim;
     uint32_t* counts;      // ring [rows][8]: S,E,I,H,R,D,pad,pad
+    uint32_t* tot;         // running totals [TOT_COPIES][8]; the Counts of the region are the column sums (mod 2^32)
     uint32_t* hosp_first;  // rank of the first vacant hospital cell in Area::iter order, or HOSP_NONE
     const Clock* clock;
     const uint64_t* draws; // injected draws table or nullptr

@@ -150,8 +150,8 @@ int epi_get_grid(epi_engine* e, uint8_t* out, uint64_t capacity, uint32_t* pitch
 
 /* ---- measurement ------------------------------------------------------------------------------------------------ */
 #define EPI_N_KERNEL_KINDS 8
-/* kinds: 0 hour kernel (propose+transition+counts), 1 commit, 2 hospital scan, 3 sleep/area-reset, 4 sweeps,
- * 5 pack, 6 unpack, 7 misc (memset etc.).  When timing is on every launch is bracketed by CUDA events on the engine's
+/* kinds: 0 hour kernel (propose + transition + counts + claim), 1 commit (lowest-id claim resolution), 2 hospital scan,
+ * 3 sleep/area-reset, 4 intervention sweeps, 5 (unused), 6 traveller pack/unpack, 7 misc.  When timing is on every launch is bracketed by CUDA events on the engine's
  * stream (this serialises nothing but adds event overhead; never on during the bench's headline timing). */
 int epi_set_kernel_timing(epi_engine* e, int on);
 int epi_get_kernel_times(epi_engine* e, double* ms_total, uint64_t* launches);
