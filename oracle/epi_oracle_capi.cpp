@@ -260,3 +260,87 @@ void orc_kat_counts(const uint32_t* st, uint32_t n, uint32_t* out7) {
 }
 
 }  // extern "C"
+
+// ---- multi-region (oracle/epi_oracle_travel.hpp) -------------------------------------------------------------------
+#include "epi_oracle_travel.hpp"
+
+extern "C" {
+
+void* orc_multi_create(const orc_config* cfgs, int n_regions, uint64_t seed, const uint32_t* migration, const uint32_t* commute, int migration_enabled,
+                       int commute_enabled, uint32_t start_migration_hour, uint32_t end_migration_hour, uint32_t extra_capacity, int threads) {
+    ORC_TRY
+    TravelPlanConfig p;
+    p.n_regions = n_regions;
+    p.migration_enabled = migration_enabled != 0;
+    p.commute_enabled = commute_enabled != 0;
+    p.migration.assign(migration, migration + (size_t)n_regions * n_regions);
+    p.commute.assign(commute, commute + (size_t)n_regions * n_regions);
+    p.start_migration_hour = start_migration_hour;
+    p.end_migration_hour = end_migration_hour;
+    MultiEngine* m = new MultiEngine();
+    m->init(std::vector<orc_config>(cfgs, cfgs + n_regions), seed, p, extra_capacity, threads);
+    return m;
+    ORC_CATCH(nullptr)
+}
+void orc_multi_destroy(void* h) { delete (MultiEngine*)h; }
+// rows: [n_regions][7]
+int orc_multi_step(void* h, uint32_t hour, uint32_t* rows) {
+    ORC_TRY
+    MultiEngine* m = (MultiEngine*)h;
+    m->step(hour);
+    for (size_t r = 0; r < m->regions.size(); ++r) counts_out(m->regions[r].counts_at_hr, rows + 7 * r);
+    return 0;
+    ORC_CATCH(1)
+}
+uint32_t orc_multi_capacity(void* h, int r) { return ((MultiEngine*)h)->regions[(size_t)r].capacity; }
+uint32_t orc_multi_population(void* h, int r) { return ((MultiEngine*)h)->regions[(size_t)r].map.current_population(); }
+// state by slot (arrays of length capacity); absent slots read st = 7, everything else 0.  reg = home region | work region << 8
+int orc_multi_get_state(void* h, int r, int32_t* cx, int32_t* cy, uint32_t* st, uint32_t* t0, uint32_t* home, uint32_t* work, uint32_t* wsa, uint32_t* reg) {
+    ORC_TRY
+    RegionEngine& e = ((MultiEngine*)h)->regions[(size_t)r];
+    for (uint32_t s = 0; s < e.capacity; ++s) { cx[s] = cy[s] = 0; st[s] = 7; t0[s] = home[s] = work[s] = wsa[s] = reg[s] = 0; }
+    const PointMap& m = e.map.current_locations;
+    for (size_t i = 0; i < m.capacity(); ++i) {
+        if (!m.used[i]) continue;
+        const Citizen& z = m.vals[i];
+        if (z.id >= e.capacity) throw std::runtime_error("agent slot out of range");
+        cx[z.id] = m.keys[i].x; cy[z.id] = m.keys[i].y;
+        st[z.id] = pack_state_word(e, z);
+        const State& s = z.state_machine.state;
+        t0[z.id] = (s.kind == Exposed || (s.kind == Infected && s.severity == Pre)) ? s.at_hour : 0;
+        home[z.id] = house_index(e.map.grid, z.home_location);
+        work[z.id] = z.work_status == NA ? 0 : office_index(e.map.grid, z.work_location);
+        wsa[z.id] = z.work_status == HospitalStaff ? z.work_start_at : 0;
+        reg[z.id] = (uint32_t)z.home_location.location_id | ((uint32_t)z.work_location.location_id << 8);
+    }
+    return 0;
+    ORC_CATCH(1)
+}
+int orc_multi_events(void* h, int r, uint32_t* events, int max_events) {
+    RegionEngine& e = ((MultiEngine*)h)->regions[(size_t)r];
+    int n = std::min<int>((int)e.events.size(), max_events);
+    for (int i = 0; i < n; ++i) { events[3 * i] = e.events[(size_t)i].hour; events[3 * i + 1] = (uint32_t)e.events[(size_t)i].kind; events[3 * i + 2] = (uint32_t)e.events[(size_t)i].status; }
+    return (int)e.events.size();
+}
+
+// engine_migration_plan.rs:120-150 known answers: percent_outgoing and the proportional allocation
+double orc_kat_percent_outgoing(const uint32_t* matrix, int n_regions, int region, uint32_t population) {
+    TravelPlanConfig p; p.n_regions = n_regions; p.migration.assign(matrix, matrix + (size_t)n_regions * n_regions);
+    return (double)p.get_total_outgoing(p.migration, region) / (double)population;
+}
+void orc_kat_alloc_outgoing(const uint32_t* matrix, int n_regions, int region, uint32_t total, uint32_t* counts_out_per_region) {
+    TravelPlanConfig p; p.n_regions = n_regions; p.migration.assign(matrix, matrix + (size_t)n_regions * n_regions);
+    const uint32_t planned_total = p.get_total_outgoing(p.migration, region);
+    uint32_t front = 0;
+    for (int to = 0; to < n_regions; ++to) {
+        counts_out_per_region[to] = 0;
+        if (to == region || p.get_outgoing(p.migration, region, to) == 0) continue;
+        const double share = (double)p.get_outgoing(p.migration, region, to) / (double)planned_total;
+        uint32_t count = (uint32_t)(int32_t)(share * (double)(int32_t)total);
+        if (count > total - front) count = total - front;
+        counts_out_per_region[to] = count;
+        front += count;
+    }
+}
+
+}  // extern "C"

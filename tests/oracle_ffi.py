@@ -252,3 +252,75 @@ def oracle_run(cfg, seed=1, mode="keyed", threads=1, max_hours=0):
     if n < 0:
         raise RuntimeError(L.orc_last_error().decode())
     return rows[:n].copy(), events[: ne.value].copy(), secs.value
+
+
+# ---- multi-region oracle (oracle/epi_oracle_travel.hpp) -----------------------------------------------------------------
+MULTI_STATE_FIELDS = STATE_FIELDS + ("reg",)
+MULTI_STATE_DTYPES = STATE_DTYPES + (np.uint32,)
+
+
+def _multi_lib():
+    L = lib()
+    if not getattr(L, "_multi_ready", False):
+        L.orc_multi_create.restype = C.c_void_p
+        L.orc_multi_create.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]
+        L.orc_multi_destroy.argtypes = [C.c_void_p]
+        L.orc_multi_step.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+        L.orc_multi_capacity.restype = C.c_uint32
+        L.orc_multi_capacity.argtypes = [C.c_void_p, C.c_int]
+        L.orc_multi_population.restype = C.c_uint32
+        L.orc_multi_population.argtypes = [C.c_void_p, C.c_int]
+        L.orc_multi_get_state.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 8
+        L.orc_multi_events.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        L.orc_kat_percent_outgoing.restype = C.c_double
+        L.orc_kat_percent_outgoing.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint32]
+        L.orc_kat_alloc_outgoing.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint32, C.c_void_p]
+        L._multi_ready = True
+    return L
+
+
+class OracleMultiEngine:
+    """R region engines in lock step with the traveller exchange (Epidemiology::run_multi_engine)."""
+
+    def __init__(self, cfgs, seed, migration=None, commute=None, start_migration_hour=0, end_migration_hour=0, extra_capacity=0, threads=1):
+        self.L = _multi_lib()
+        self.R = len(cfgs)
+        arr = (EpiConfig * self.R)(*cfgs)
+        mig = np.ascontiguousarray(migration if migration is not None else np.zeros((self.R, self.R)), np.uint32)
+        com = np.ascontiguousarray(commute if commute is not None else np.zeros((self.R, self.R)), np.uint32)
+        self.h = self.L.orc_multi_create(C.cast(arr, C.c_void_p), self.R, seed, _ptr(mig), _ptr(com), int(migration is not None), int(commute is not None),
+                                         start_migration_hour, end_migration_hour, extra_capacity, threads)
+        if not self.h:
+            raise RuntimeError(self.L.orc_last_error().decode())
+
+    def close(self):
+        if self.h:
+            self.L.orc_multi_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def step(self, hour):
+        rows = np.zeros((self.R, 7), np.uint32)
+        if self.L.orc_multi_step(self.h, hour, _ptr(rows)):
+            raise RuntimeError(self.L.orc_last_error().decode())
+        return rows
+
+    def capacity(self, r):
+        return self.L.orc_multi_capacity(self.h, r)
+
+    def population(self, r):
+        return self.L.orc_multi_population(self.h, r)
+
+    def get_state(self, r):
+        n = self.capacity(r)
+        arrs = {f: np.zeros(n, dt) for f, dt in zip(MULTI_STATE_FIELDS, MULTI_STATE_DTYPES)}
+        if self.L.orc_multi_get_state(self.h, r, *[_ptr(arrs[f]) for f in MULTI_STATE_FIELDS]):
+            raise RuntimeError(self.L.orc_last_error().decode())
+        return arrs
+
+    def events(self, r):
+        ev = np.zeros((64, 3), np.uint32)
+        n = self.L.orc_multi_events(self.h, r, _ptr(ev), 64)
+        return ev[:n]
