@@ -50,13 +50,25 @@ class EpiConfig(C.Structure):
     ]
 
 
+class EpiTravelPlan(C.Structure):
+    """`epi_travel_plan` of include/epi.h (common::config::TravelPlanConfig, regions named by index)."""
+
+    _fields_ = [("n_regions", C.c_int32), ("migration_enabled", C.c_int32), ("commute_enabled", C.c_int32), ("migration", C.c_void_p),
+                ("commute", C.c_void_p), ("start_migration_hour", C.c_uint32), ("end_migration_hour", C.c_uint32)]
+
+
+TRAVEL_RECORD_BYTES = 32
+TRAVEL_MIGRATE, TRAVEL_COMMUTE = 0, 1
+
+
 class EpiCounts(C.Structure):
     _fields_ = [(n, C.c_uint32) for n in ("hour", "susceptible", "exposed", "infected", "hospitalized", "recovered", "deceased")]
 
 
 # every symbol include/epi.h declares (tests/test_abi.py checks the library exports all of them)
 EXPORTS = [
-    "epi_create", "epi_create_region", "epi_destroy", "epi_last_error", "epi_population", "epi_counts_at_start", "epi_set_stream",
+    "epi_create", "epi_create_region", "epi_create_multi", "epi_destroy", "epi_last_error", "epi_population", "epi_capacity", "epi_counts_at_start",
+    "epi_set_stream", "epi_travel_pack", "epi_travel_unpack", "epi_finish_hour", "epi_get_regions",
     "epi_sync", "epi_reset", "epi_step", "epi_step_with_draws", "epi_run_hours", "epi_simulate_hours", "epi_intervention_events", "epi_lock_city", "epi_unlock_city", "epi_vaccinate",
     "epi_expand_hospital", "epi_get_state", "epi_set_state", "epi_geometry", "epi_get_grid", "epi_set_kernel_timing",
     "epi_get_kernel_times", "epi_launch_count", "epi_device_bytes", "epi_config_from_json", "epi_config_from_json_string",
@@ -79,6 +91,13 @@ def load():
     vp, u32, u64, i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int
     L.epi_create.argtypes = [C.POINTER(EpiConfig), u64, i32, C.POINTER(vp)]
     L.epi_create_region.argtypes = [C.POINTER(EpiConfig), u64, i32, i32, C.POINTER(vp)]
+    L.epi_create_multi.argtypes = [C.POINTER(EpiConfig), u64, i32, i32, C.POINTER(EpiTravelPlan), u32, C.POINTER(vp)]
+    L.epi_capacity.argtypes = [vp]
+    L.epi_capacity.restype = u32
+    L.epi_travel_pack.argtypes = [vp, u32, i32, vp, u64, vp]
+    L.epi_travel_unpack.argtypes = [vp, u32, i32, vp, vp]
+    L.epi_finish_hour.argtypes = [vp, u32, C.POINTER(EpiCounts)]
+    L.epi_get_regions.argtypes = [vp, vp]
     L.epi_destroy.argtypes = [vp]
     L.epi_destroy.restype = None
     L.epi_last_error.argtypes = [vp]

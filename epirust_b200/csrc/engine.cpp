@@ -239,8 +239,8 @@ int run_chunk(epi_engine* e, uint32_t first_hour, uint32_t n, bool inject, epi_c
         } else e->last_counts.hour = first_hour + k;  // sleep hour: nothing observable changed (citizen/mod.rs:244-248)
         out[k] = e->last_counts;
         const uint64_t total = (uint64_t)out[k].susceptible + out[k].exposed + out[k].infected + out[k].hospitalized + out[k].recovered + out[k].deceased;
-        if (total != e->P.n)  // allocation_map.rs:128 assert_eq!(csv_record.total(), current_population)
-            return engine_fail(e, EPI_ERR_STATE, "counts total " + std::to_string(total) + " != population " + std::to_string(e->P.n) + " at hour " + std::to_string(first_hour + k));
+        if (total != e->population)  // allocation_map.rs:128 assert_eq!(csv_record.total(), current_population)
+            return engine_fail(e, EPI_ERR_STATE, "counts total " + std::to_string(total) + " != population " + std::to_string(e->population) + " at hour " + std::to_string(first_hour + k));
     }
     return EPI_OK;
 }
@@ -253,6 +253,8 @@ int upload_agents(epi_engine* e, const HostAgents& a) {
     CU(cudaMemcpyAsync(e->D.home, a.home.data(), nb, cudaMemcpyHostToDevice, e->stream));
     CU(cudaMemcpyAsync(e->D.work, a.work.data(), nb, cudaMemcpyHostToDevice, e->stream));
     CU(cudaMemcpyAsync(e->D.wsa, a.wsa.data(), nb, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemcpyAsync(e->D.reg, a.reg.data(), nb, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemsetAsync(e->D.prop, 0, nb, e->stream));
     CU(cudaStreamSynchronize(e->stream));
     return EPI_OK;
 }
@@ -265,7 +267,27 @@ int snapshot_initial(epi_engine* e) {
     CU(cudaMemcpyAsync(e->i_home, e->D.home, nb, cudaMemcpyDeviceToDevice, e->stream));
     CU(cudaMemcpyAsync(e->i_work, e->D.work, nb, cudaMemcpyDeviceToDevice, e->stream));
     CU(cudaMemcpyAsync(e->i_wsa, e->D.wsa, nb, cudaMemcpyDeviceToDevice, e->stream));
+    CU(cudaMemcpyAsync(e->i_reg, e->D.reg, nb, cudaMemcpyDeviceToDevice, e->stream));
     return EPI_OK;
+}
+
+// host bookkeeping of the exchange back to its initial state
+void reset_travel_state(epi_engine* e) {
+    e->population = e->cfg.number_of_agents;
+    e->free_slots = e->free_slots0;
+    if (!e->multi) return;
+    e->houses_occupancy.init(e->geo.n_houses);
+    e->offices_occupancy.init(e->geo.n_offices);
+    // set_start_locations_and_occupancies (grid.rs:125-155): houses with residents and every office enter the heaps
+    for (uint32_t i = 0; i < e->geo.n_houses; ++i)
+        if (e->house_count0[i] > 0) {
+            const uint32_t o = house_origin(e->geo, i);
+            e->houses_occupancy.push(i, e->house_count0[i], (int)(o & CELL_XMASK), (int)(o >> CELL_BITS));
+        }
+    for (uint32_t i = 0; i < e->geo.n_offices; ++i) {
+        const uint32_t o = office_origin(e->geo, i);
+        e->offices_occupancy.push(i, e->office_count0[i], (int)(o & CELL_XMASK), (int)(o >> CELL_BITS));
+    }
 }
 
 void initial_counts(epi_engine* e) {
@@ -288,14 +310,23 @@ const char* epi_last_error(const epi_engine* e) {
     return copy.c_str();
 }
 
-int epi_create(const epi_config* cfg, uint64_t seed, int device, epi_engine** out) { return epi_create_region(cfg, seed, device, 0, out); }
+int epi_create(const epi_config* cfg, uint64_t seed, int device, epi_engine** out) { return epi_create_multi(cfg, seed, device, 0, nullptr, 0, out); }
 
 int epi_create_region(const epi_config* cfg, uint64_t seed, int device, int region, epi_engine** out) {
+    return epi_create_multi(cfg, seed, device, region, nullptr, 0, out);
+}
+
+int epi_create_multi(const epi_config* cfg, uint64_t seed, int device, int region, const epi_travel_plan* plan, uint32_t extra_capacity, epi_engine** out) {
     if (!cfg || !out) return engine_fail(nullptr, EPI_ERR_ARG, "null argument");
     *out = nullptr;
     const std::string bad = validate_config(*cfg);
     if (!bad.empty()) return engine_fail(nullptr, EPI_ERR_CONFIG, bad);
-    if (region < 0 || region > 255) return engine_fail(nullptr, EPI_ERR_ARG, "region must be in 0..255");
+    if (region < 0 || region > 254) return engine_fail(nullptr, EPI_ERR_ARG, "region must be in 0..254");
+    if (plan) {
+        if (plan->n_regions < 1 || plan->n_regions > 255 || region >= plan->n_regions) return engine_fail(nullptr, EPI_ERR_ARG, "travel plan: bad n_regions / region");
+        if ((plan->migration_enabled && !plan->migration) || (plan->commute_enabled && !plan->commute)) return engine_fail(nullptr, EPI_ERR_ARG, "travel plan: enabled matrix is null");
+    }
+    if ((uint64_t)cfg->number_of_agents + extra_capacity > (1u << 27)) return engine_fail(nullptr, EPI_ERR_CONFIG, "agent slots must be <= 2^27");
     int n_dev = 0;
     cudaError_t cr = cudaGetDeviceCount(&n_dev);
     if (cr != cudaSuccess || n_dev == 0)
@@ -319,6 +350,40 @@ int epi_create_region(const epi_config* cfg, uint64_t seed, int device, int regi
         e->P = make_params(*cfg, e->geo, seed, region);
         HostAgents agents;
         build_population(*cfg, e->geo, seed, region, agents);
+        const uint32_t n_agents = cfg->number_of_agents, capacity = n_agents + extra_capacity;
+        if (plan) {
+            e->multi = true;
+            e->n_regions = plan->n_regions;
+            e->migration_enabled = plan->migration_enabled != 0;
+            e->commute_enabled = plan->commute_enabled != 0;
+            e->start_migration_hour = plan->start_migration_hour;
+            e->end_migration_hour = plan->end_migration_hour;
+            const size_t R = (size_t)plan->n_regions;
+            e->migration_row.assign(R, 0);
+            e->commute_row.assign(R, 0);
+            if (e->migration_enabled) e->migration_row.assign(plan->migration + (size_t)region * R, plan->migration + (size_t)(region + 1) * R);
+            if (e->commute_enabled) {
+                e->commute_row.assign(plan->commute + (size_t)region * R, plan->commute + (size_t)(region + 1) * R);
+                apply_commute_plan(agents, n_agents, region, e->commute_row);
+            }
+            e->house_count0.assign(e->geo.n_houses, 0);
+            e->office_count0.assign(e->geo.n_offices, 0);
+            for (uint32_t i = 0; i < n_agents; ++i) {
+                e->house_count0[house_index_of(e->geo, agents.home[i])]++;
+                const bool working = ((agents.st[i] >> ST_WS_SHIFT) & 3u) != WS_NA;
+                if (working && ((agents.reg[i] >> 8) & 0xFFu) == (uint32_t)region) e->office_count0[office_index_of(e->geo, agents.work[i])]++;
+            }
+        }
+        // empty slots for arrivals
+        agents.resize(capacity);
+        for (uint32_t i = n_agents; i < capacity; ++i) { agents.st[i] = ST_ABSENT; agents.cell[i] = agents.t0[i] = agents.home[i] = agents.work[i] = agents.wsa[i] = agents.reg[i] = 0; }
+        e->free_slots0.clear();
+        for (uint32_t sl = capacity; sl-- > n_agents;) e->free_slots0.push_back(sl);  // pop order: n, n+1, ...
+        e->P.n = capacity;
+        uint32_t bits = 1;
+        while ((1ull << bits) < (uint64_t)capacity) ++bits;
+        e->P.id_bits = bits;
+        reset_travel_state(e);
         if (cudaSetDevice(device) != cudaSuccess) { e->err = "cudaSetDevice failed"; return fail(EPI_ERR_CUDA); }
         if (cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) != cudaSuccess) { e->err = "cudaStreamCreate failed"; return fail(EPI_ERR_CUDA); }
         e->stream = e->own_stream;
@@ -331,6 +396,9 @@ int epi_create_region(const epi_config* cfg, uint64_t seed, int device, int regi
         ok &= dev_alloc(e, &e->D.work, n) == cudaSuccess;
         ok &= dev_alloc(e, &e->D.wsa, n) == cudaSuccess;
         ok &= dev_alloc(e, &e->D.prop, n) == cudaSuccess;
+        ok &= dev_alloc(e, &e->D.reg, n) == cudaSuccess;
+        ok &= dev_alloc(e, &e->i_reg, n) == cudaSuccess;
+        ok &= cudaMallocHost((void**)&e->h_small, 64 * sizeof(uint32_t)) == cudaSuccess;
         ok &= dev_alloc(e, &e->grid_alloc, grid_alloc_bytes(e)) == cudaSuccess;
         e->D.grid = e->grid_alloc ? e->grid_alloc + (size_t)e->geo.pitch * GRID_YPAD + GRID_XPAD : nullptr;
         ok &= dev_alloc(e, &e->D.claim, cells) == cudaSuccess;
@@ -371,14 +439,17 @@ void epi_destroy(epi_engine* e) {
     drop_graph(e);
     for (auto& pe : e->pending_events) { cudaEventDestroy(pe.second.first); cudaEventDestroy(pe.second.second); }
     void* ptrs[] = {e->D.cell, e->D.st, e->D.t0, e->D.home, e->D.work, e->D.wsa, e->D.prop, e->grid_alloc, e->D.claim, e->D.counts, e->D.tot,
-                    e->d_clock, e->d_misc, e->d_draws, e->i_cell, e->i_st, e->i_t0, e->i_home, e->i_work, e->i_wsa};
+                    e->d_clock, e->d_misc, e->d_draws, e->i_cell, e->i_st, e->i_t0, e->i_home, e->i_work, e->i_wsa, e->D.reg, e->i_reg,
+                    e->t_block_counts, e->t_total, e->t_out_slots, e->t_out_dest, e->t_idx, e->t_table_keys, e->t_table_vals, e->t_placed};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (e->h_counts) cudaFreeHost(e->h_counts);
+    if (e->h_small) cudaFreeHost(e->h_small);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     delete e;
 }
 
-uint32_t epi_population(const epi_engine* e) { return e ? e->P.n : 0; }
+uint32_t epi_population(const epi_engine* e) { return e ? e->population : 0; }
+uint32_t epi_capacity(const epi_engine* e) { return e ? e->P.n : 0; }
 
 int epi_counts_at_start(const epi_engine* e, epi_counts* out) {
     if (!e || !out) return engine_fail(e, EPI_ERR_ARG, "null argument");
@@ -414,6 +485,9 @@ int epi_reset(epi_engine* e) {
     CU(cudaMemcpyAsync(e->D.home, e->i_home, nb, cudaMemcpyDeviceToDevice, e->stream));
     CU(cudaMemcpyAsync(e->D.work, e->i_work, nb, cudaMemcpyDeviceToDevice, e->stream));
     CU(cudaMemcpyAsync(e->D.wsa, e->i_wsa, nb, cudaMemcpyDeviceToDevice, e->stream));
+    CU(cudaMemcpyAsync(e->D.reg, e->i_reg, nb, cudaMemcpyDeviceToDevice, e->stream));
+    CU(cudaMemsetAsync(e->D.prop, 0, nb, e->stream));
+    reset_travel_state(e);
     if (e->P.hospital_gen != 0) { e->P.hospital_gen = 0; drop_graph(e); }
     initial_counts(e);
     e->interventions = epi::Interventions(e->cfg);
@@ -504,6 +578,7 @@ int epi_get_state(epi_engine* e, int32_t* cx, int32_t* cy, uint32_t* st, uint32_
         cy[i] = (int32_t)(cell[i] >> CELL_BITS);
         // canonical form: fields that the reference's enum variant does not carry read as 0
         const uint32_t state = st[i] & ST_STATE_MASK, sev = (st[i] >> ST_SEV_SHIFT) & 3u, ws = (st[i] >> ST_WS_SHIFT) & 3u;
+        if (state == ST_ABSENT) { cx[i] = cy[i] = 0; st[i] = ST_ABSENT; t0[i] = home[i] = work[i] = wsa[i] = 0; continue; }
         if (!(state == ST_E || (state == ST_I && sev == SEV_PRE))) t0[i] = 0;
         home[i] = house_index_of(e->geo, home[i]);
         work[i] = ws == WS_NA ? 0u : office_index_of(e->geo, work[i]);
@@ -515,11 +590,13 @@ int epi_get_state(epi_engine* e, int32_t* cx, int32_t* cy, uint32_t* st, uint32_
 int epi_set_state(epi_engine* e, uint32_t n, const int32_t* cx, const int32_t* cy, const uint32_t* st, const uint32_t* t0, const uint32_t* home,
                   const uint32_t* work, const uint32_t* wsa) {
     if (!e || !cx || !cy || !st || !t0 || !home || !work || !wsa) return engine_fail(e, EPI_ERR_ARG, "null argument");
-    if (n != e->P.n) return engine_fail(e, EPI_ERR_ARG, "epi_set_state: n must equal epi_population()");
+    if (n != e->P.n) return engine_fail(e, EPI_ERR_ARG, "epi_set_state: n must equal epi_capacity()");
+    if (e->multi) return engine_fail(e, EPI_ERR_STATE, "epi_set_state is not available on a multi-region engine");
     CU(cudaSetDevice(e->device));
     HostAgents a;
     a.resize(n);
     for (uint32_t i = 0; i < n; ++i) {
+        a.reg[i] = (uint32_t)e->P.region | ((uint32_t)e->P.region << 8);
         if (cx[i] < 0 || cy[i] < 0 || (uint32_t)cx[i] >= e->geo.pitch || (uint32_t)cy[i] >= e->geo.rows)
             return engine_fail(e, EPI_ERR_ARG, "epi_set_state: cell outside the grid");
         const uint32_t ws = (st[i] >> ST_WS_SHIFT) & 3u;
@@ -534,6 +611,18 @@ int epi_set_state(epi_engine* e, uint32_t n, const int32_t* cx, const int32_t* c
     int rc = upload_agents(e, a);
     if (rc) return rc;
     return rebuild_grid(e);
+}
+
+int epi_get_regions(epi_engine* e, uint32_t* reg) {
+    if (!e || !reg) return engine_fail(e, EPI_ERR_ARG, "null argument");
+    CU(cudaSetDevice(e->device));
+    std::vector<uint32_t> st(e->P.n);
+    CU(cudaMemcpyAsync(reg, e->D.reg, (size_t)e->P.n * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaMemcpyAsync(st.data(), e->D.st, (size_t)e->P.n * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    for (uint32_t i = 0; i < e->P.n; ++i)
+        if ((st[i] & ST_STATE_MASK) == ST_ABSENT) reg[i] = 0;
+    return EPI_OK;
 }
 
 int epi_geometry(const epi_engine* e, int32_t* out) {

@@ -78,6 +78,22 @@ std::string validate_config(const epi_config& c) {
     return "";
 }
 
+void apply_commute_plan(HostAgents& a, uint32_t n_agents, int region, const std::vector<uint32_t>& commute_row) {
+    uint32_t i = 0;
+    for (size_t to = 0; to < commute_row.size(); ++to) {
+        uint32_t want = commute_row[to];
+        while (want > 0 && i < n_agents) {
+            const uint32_t s = a.st[i];
+            const bool working = ((s >> ST_WS_SHIFT) & 3u) != WS_NA;
+            if (working && ((a.reg[i] >> 8) & 0xFFu) == (uint32_t)region && (s & ST_PT)) {
+                a.reg[i] = (a.reg[i] & 0xFFu) | ((uint32_t)to << 8);
+                --want;
+            }
+            ++i;
+        }
+    }
+}
+
 Params make_params(const epi_config& c, const Geometry& g, uint64_t seed, int region) {
     Params P{};
     P.n = c.number_of_agents;
@@ -149,6 +165,7 @@ void build_population(const epi_config& c, const Geometry& g, uint64_t seed, int
         out.home[i] = house_origin(g, i % g.n_houses);
         out.work[i] = working ? office_origin(g, i % g.n_offices) : 0u;
         out.wsa[i] = ws == WS_STAFF ? kRoutineWorkTime : 0u;
+        out.reg[i] = (uint32_t)region | ((uint32_t)region << 8);
     }
 
     // starting infections: uniform without replacement, then exposed / asymptomatic / mild / severe in that order

@@ -39,14 +39,18 @@ inline uint32_t office_index_of(const Geometry& g, uint32_t origin) {
 }
 
 struct HostAgents {
-    std::vector<uint32_t> cell, st, t0, home, work, wsa;
+    std::vector<uint32_t> cell, st, t0, home, work, wsa, reg;
     size_t size() const { return st.size(); }
-    void resize(size_t n) { cell.resize(n); st.resize(n); t0.resize(n); home.resize(n); work.resize(n); wsa.resize(n); }
+    void resize(size_t n) { cell.resize(n); st.resize(n); t0.resize(n); home.resize(n); work.resize(n); wsa.resize(n); reg.resize(n); }
 };
 
 // Grid::generate_population + citizen_factory + set_starting_infections + init_interventions' essential workers
 // (grid.rs:83-155, citizen_factory.rs:31-134, epidemiology_simulation.rs:178-192).  Throws std::runtime_error.
 void build_population(const epi_config& cfg, const Geometry& geo, uint64_t seed, int region, HostAgents& out);
+
+// citizen_factory::update_commuters (citizen_factory.rs:90-110): the first sum(commute_row) working public-transport users
+// in creation order get the row's regions as work region (row order, commute_row[to] agents each)
+void apply_commute_plan(HostAgents& agents, uint32_t n_agents, int region, const std::vector<uint32_t>& commute_row);
 
 // Params for the kernels from config + geometry
 Params make_params(const epi_config& cfg, const Geometry& geo, uint64_t seed, int region);

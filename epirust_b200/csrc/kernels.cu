@@ -31,6 +31,7 @@
 #include "kernels.h"
 #include "layout.h"
 #include "philox.cuh"
+#include "agent.cuh"
 
 namespace epi {
 
@@ -58,21 +59,6 @@ __device__ __forceinline__ Rect origin_rect(uint32_t packed, int size_minus_1) {
     r.ex = r.sx + size_minus_1;
     r.ey = r.sy + size_minus_1;
     return r;
-}
-
-// Disease::get_current_transmission_rate as a class (common/src/disease/mod.rs:88-95); d = (day + immunity) as u32, wrapping
-__device__ __forceinline__ uint32_t rate_class(const Params& P, uint32_t d) {
-    if (P.regular_start < d && d <= P.high_start) return 1;
-    if (P.high_start < d && d <= P.last_day) return 2;
-    return 0;
-}
-// what other agents can see of this agent: occupied + Citizen::get_infection_transmission_rate for infected && !hospitalized
-__device__ __forceinline__ uint32_t cell_byte(const Params& P, uint32_t s) {
-    if ((s & ST_STATE_MASK) == ST_I && !(s & ST_HOSP)) {
-        const int day = (int)(s >> ST_DAY_SHIFT), imm = (int)((s >> ST_IMM_SHIFT) & 7u) - 2;
-        return 1u + rate_class(P, (uint32_t)(day + imm));
-    }
-    return 1u;
 }
 
 // The 8 Moore neighbours of a cell in the reference's iterator order (geography/point.rs:59):
@@ -217,11 +203,6 @@ __device__ __forceinline__ void block_count(uint32_t cat, uint32_t* __restrict__
     __syncthreads();
     if (threadIdx.x < 6 && s_cnt[threadIdx.x]) atomicAdd(&out_row[threadIdx.x], s_cnt[threadIdx.x]);
 }
-__device__ __forceinline__ uint32_t count_category(uint32_t s) {
-    const uint32_t st = s & ST_STATE_MASK;  // order of the CSV columns: S,E,I,H,R,D
-    return st == ST_S ? 0u : st == ST_E ? 1u : st == ST_I ? ((s & ST_HOSP) ? 3u : 2u) : st == ST_R ? 4u : 5u;
-}
-
 __global__ void __launch_bounds__(256) k_hospital_scan(Params P, const uint8_t* __restrict__ grid, uint32_t* __restrict__ hosp_first) {
     const Rect h = P.hospital();
     const uint32_t w = (uint32_t)(h.ex - h.sx + 1), nh = (uint32_t)(h.ey - h.sy + 1);
@@ -243,6 +224,7 @@ __global__ void __launch_bounds__(256, KIND == KIND_MOVE ? 5 : 4) k_hour(Params 
     const uint32_t hm = ld_early(D.home + i);
     const uint32_t wk = KIND == KIND_MOVE ? ld_early(D.work + i) : 0u;
     const uint32_t hour = D.clock->hour_base + hour_offset;
+    if ((s0 & ST_STATE_MASK) == ST_ABSENT) return;  // empty slot; its prop word stays 0
     const int x = (int)(c0 & CELL_XMASK), y = (int)(c0 >> CELL_BITS);
     const uint8_t* __restrict__ grid = D.grid;
     uint32_t s = s0;
@@ -468,7 +450,7 @@ __global__ void __launch_bounds__(256) k_sleep(Params P, DevPtrs D, uint32_t hou
     uint32_t cat = 6;
     if (i < P.n) {
         uint32_t s = D.st[i];
-        if (((s >> ST_WS_SHIFT) & 3u) != WS_STAFF && (s & ST_AREA_MASK) != (AK_HOME << ST_AREA_SHIFT)) {
+        if ((s & ST_STATE_MASK) != ST_ABSENT && ((s >> ST_WS_SHIFT) & 3u) != WS_STAFF && (s & ST_AREA_MASK) != (AK_HOME << ST_AREA_SHIFT)) {
             s = (s & ~ST_AREA_MASK) | (AK_HOME << ST_AREA_SHIFT);
             D.st[i] = s;
         }
@@ -489,13 +471,13 @@ __global__ void __launch_bounds__(256) k_lock(Params P, uint32_t* __restrict__ s
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n) return;
     const uint32_t s = st[i];
-    if (((s >> ST_WS_SHIFT) & 3u) != WS_ESSENTIAL && !(s & ST_ISO)) st[i] = s | ST_ISO;
+    if ((s & ST_STATE_MASK) != ST_ABSENT && ((s >> ST_WS_SHIFT) & 3u) != WS_ESSENTIAL && !(s & ST_ISO)) st[i] = s | ST_ISO;
 }
 __global__ void __launch_bounds__(256) k_unlock(Params P, uint32_t* __restrict__ st) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n) return;
     const uint32_t s = st[i];
-    if (s & ST_ISO) st[i] = s & ~ST_ISO;
+    if ((s & ST_STATE_MASK) != ST_ABSENT && (s & ST_ISO)) st[i] = s & ~ST_ISO;
 }
 __global__ void __launch_bounds__(256) k_vaccinate(Params P, uint32_t* __restrict__ st, uint64_t thr, uint32_t hour) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -509,6 +491,7 @@ __global__ void __launch_bounds__(256) k_build_grid(Params P, const uint32_t* __
                                                      uint32_t* __restrict__ collisions) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n) return;
+    if ((st[i] & ST_STATE_MASK) == ST_ABSENT) return;
     const uint32_t c = cell[i];
     const size_t at = (size_t)(c >> CELL_BITS) * P.pitch + (c & CELL_XMASK);
     // byte-wide check-and-set through the containing word (grid base and pitch are 4-byte aligned)

@@ -18,16 +18,14 @@
 //   claim[cells] u32  (stamp << id_bits) | (id_mask - agent id), atomicMax: lowest agent id wins the cell this hour
 #pragma once
 #include <stdint.h>
-#if !defined(__CUDACC__)
-#define __host__
-#define __device__
-#endif
+#include <cuda_runtime.h>
 
 namespace epi {
 
 // ---- agent state word ------------------------------------------------------------------------------------------
 enum : uint32_t {
     ST_S = 0, ST_E = 1, ST_I = 2, ST_R = 3, ST_D = 4,               // state_machine/state.rs:31-37
+    ST_ABSENT = 7,                                                   // empty agent slot (multi-region engines: travellers leave and arrive)
     SEV_PRE = 0, SEV_ASYM = 1, SEV_MILD = 2, SEV_SEVERE = 3,         // state_machine/state.rs:22-28
     WS_NORMAL = 0, WS_ESSENTIAL = 1, WS_STAFF = 2, WS_NA = 3,        // citizen/work_status.rs:22-28
     AK_HOME = 0, AK_WORK = 1, AK_TRANSPORT = 2, AK_HOUSING = 3, AK_HOSPITAL0 = 4, AK_HOSPITAL1 = 5,  // Citizen.current_area
@@ -70,7 +68,7 @@ struct Rect {
 
 // run constants, passed by value to every kernel
 struct Params {
-    uint32_t n;        // agents
+    uint32_t n;        // agent slots (== population for a standalone engine; slots whose state is ST_ABSENT are empty)
     int grid_size;     // G: is_point_in_grid is 0 <= x,y < G (allocation_map.rs:156-159)
     uint32_t pitch;    // bytes per grid row
     uint32_t rows;
@@ -96,6 +94,25 @@ struct Params {
     __host__ __device__ const Rect& hospital() const { return zone[2 + hospital_gen]; }
 };
 
+// one traveller on the wire (engine/src/travel/commute/commuter.rs:26-35, migration/migrator.rs:25-32): 8 words
+struct TravelRecord {
+    uint32_t st;    // packed state word of the sender (state, severity, day, immunity, vaccinated, uses_public_transport, work status)
+    uint32_t t0;    // at_hour of Exposed / Pre
+    uint32_t home;  // Commuter.home_location origin (meaningless for a Migrator: the receiver assigns a house)
+    uint32_t work;  // Commuter.work_location origin
+    uint32_t reg;   // home region | work region << 8
+    uint32_t slot;  // the sender's slot (informational, like the reference's Uuid)
+    uint32_t from;  // sending region
+    uint32_t pad;
+};
+
+enum : int { TRAVEL_MIGRATE = 0, TRAVEL_COMMUTE = 1 };
+struct TravelArgs {
+    int kind;               // TRAVEL_MIGRATE (h % 24 == 0) or TRAVEL_COMMUTE (h % 24 in {7, 17})
+    uint32_t hour, hour_of_day;
+    uint64_t thr_outgoing;  // Bernoulli threshold of EngineMigrationPlan::percent_outgoing
+};
+
 struct Clock {           // device-resident so CUDA graphs can be replayed for any day
     uint32_t hour_base;  // kernels run hour = hour_base + offset
     uint32_t epoch_base; // claim stamp = hour - epoch_base + 1
@@ -105,6 +122,7 @@ struct Clock {           // device-resident so CUDA graphs can be replayed for a
 
 struct DevPtrs {
     uint32_t *cell, *st, *t0, *home, *work, *wsa, *prop;
+    uint32_t* reg;         // home region | work region << 8 (Area.location_id of home_location / work_location); travel kernels only
     uint8_t* grid;
     uint32_t* claim;
     uint32_t* counts;      // ring [rows][8]: S,E,I,H,R,D,pad,pad

@@ -53,6 +53,43 @@ static void log_counts(const epi_counts& c) {
     std::printf("INFO - S: %u, E:%u, I: %u, H: %u, R: %u, D: %u\n", c.susceptible, c.exposed, c.infected, c.hospitalized, c.recovered, c.deceased);
 }
 
+// CitizenLocationMap::process_interventions (allocation_map.rs:306-337) on the Counts row of one hour; in a multi-region
+// engine also stop_simulation's MultiEngine arm (epidemiology_simulation.rs:564-571)
+int process_interventions(epi_engine* e, const epi_counts& c, bool log) {
+    Interventions& iv = e->interventions;
+    int rc = EPI_OK;
+    if (const double* pct = iv.vaccinate.get_vaccination_percentage(c)) {
+        if (log) std::printf("INFO - Vaccination\n");
+        rc = epi_vaccinate(e, *pct, c.hour);
+        if (rc) return rc;
+        e->events.push_back({c.hour, 1, 0});
+    }
+    if (iv.lockdown.should_apply(c)) {
+        iv.lockdown.apply();
+        if (log) std::printf("INFO - Locking the city. Hour: %u\n", c.hour);
+        rc = epi_lock_city(e);
+        if (rc) return rc;
+        e->events.push_back({c.hour, 0, 1});
+    }
+    if (iv.lockdown.should_unlock(c)) {
+        if (log) std::printf("INFO - Unlocking city. Hour: %u\n", c.hour);
+        rc = epi_unlock_city(e);
+        if (rc) return rc;
+        iv.lockdown.unapply();
+        e->events.push_back({c.hour, 0, 0});
+    }
+    iv.build_new_hospital.counts_updated(c);
+    if (iv.build_new_hospital.should_apply(c)) {
+        if (log) std::printf("INFO - Increasing the hospital size\n");
+        rc = epi_expand_hospital(e);
+        if (rc) return rc;
+        iv.build_new_hospital.apply();
+        e->events.push_back({c.hour, 2, 0});
+    }
+    if (e->multi && iv.lockdown.is_locked_down() && c.exposed == 0 && c.infected == 0 && c.hospitalized == 0) iv.lockdown.set_zero_infection_hour(c.hour);
+    return EPI_OK;
+}
+
 // hours [first_hour, first_hour + n_hours): simulate + process_interventions (+ stop rule)
 static int simulate_hours(epi_engine* e, uint32_t first_hour, uint32_t n_hours, bool stop_rule, epi_counts* rows_out, uint32_t* n_rows, int* stopped,
                           bool log, const std::chrono::steady_clock::time_point* start_time) {
@@ -76,37 +113,10 @@ static int simulate_hours(epi_engine* e, uint32_t first_hour, uint32_t n_hours, 
         for (uint32_t k = 0; k < n && !stop; ++k) {
             const epi_counts& c = seg[k];  // counts_at_hr.increment_hour() + simulate()
             rows_out[written++] = c;       // listeners.counts_updated
-            // CitizenLocationMap::process_interventions (allocation_map.rs:306-337)
-            if (const double* pct = iv.vaccinate.get_vaccination_percentage(c)) {
-                if (log) std::printf("INFO - Vaccination\n");
-                rc = epi_vaccinate(e, *pct, c.hour);
-                if (rc) return rc;
-                e->events.push_back({c.hour, 1, 0});
-            }
-            if (iv.lockdown.should_apply(c)) {
-                iv.lockdown.apply();
-                if (log) std::printf("INFO - Locking the city. Hour: %u\n", c.hour);
-                rc = epi_lock_city(e);
-                if (rc) return rc;
-                e->events.push_back({c.hour, 0, 1});
-            }
-            if (iv.lockdown.should_unlock(c)) {
-                if (log) std::printf("INFO - Unlocking city. Hour: %u\n", c.hour);
-                rc = epi_unlock_city(e);
-                if (rc) return rc;
-                iv.lockdown.unapply();
-                e->events.push_back({c.hour, 0, 0});
-            }
-            iv.build_new_hospital.counts_updated(c);
-            if (iv.build_new_hospital.should_apply(c)) {
-                if (log) std::printf("INFO - Increasing the hospital size\n");
-                rc = epi_expand_hospital(e);
-                if (rc) return rc;
-                iv.build_new_hospital.apply();
-                e->events.push_back({c.hour, 2, 0});
-            }
+            rc = process_interventions(e, c, log);
+            if (rc) return rc;
             // Epidemiology::stop_simulation, Standalone arm (epidemiology_simulation.rs:564-575)
-            if (stop_rule && c.exposed == 0 && c.infected == 0 && c.hospitalized == 0) stop = true;
+            if (stop_rule && !e->multi && c.exposed == 0 && c.infected == 0 && c.hospitalized == 0) stop = true;
             if (!stop && c.hour % 100u == 0 && log && start_time) {
                 const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - *start_time).count();
                 std::printf("INFO - Throughput: %f iterations/sec; simulation hour %u\n", (double)c.hour / el, c.hour);

@@ -103,6 +103,9 @@ struct RunResult {
     std::string csv_path, interventions_path;
 };
 
+// process_interventions on one Counts row (host decisions + the sweep kernels)
+int process_interventions(epi_engine* e, const epi_counts& c, bool log);
+
 // Epidemiology::run_single_engine on an existing engine (epidemiology_simulation.rs:211-274).  Returns EPI_* code.
 int run_single_engine(epi_engine* e, const epi_config& cfg, RunResult& result, bool log);
 

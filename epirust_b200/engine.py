@@ -83,11 +83,22 @@ class EpiError(RuntimeError):
 class Engine:
     """One region engine resident on one GPU (`epi_engine`)."""
 
-    def __init__(self, cfg, seed=1, device=0, region=0):
+    def __init__(self, cfg, seed=1, device=0, region=0, plan=None, extra_capacity=0):
+        """plan: None (standalone) or dict(n_regions, migration=RxR or None, commute=RxR or None, start_migration_hour, end_migration_hour)."""
         self.L = _ffi.load()
         self.cfg = cfg
         h = C.c_void_p()
-        rc = self.L.epi_create_region(C.byref(cfg), seed, device, region, C.byref(h))
+        if plan is None:
+            rc = self.L.epi_create_region(C.byref(cfg), seed, device, region, C.byref(h))
+        else:
+            R = int(plan["n_regions"])
+            self._mig = np.ascontiguousarray(plan.get("migration") if plan.get("migration") is not None else np.zeros((R, R)), np.uint32)
+            self._com = np.ascontiguousarray(plan.get("commute") if plan.get("commute") is not None else np.zeros((R, R)), np.uint32)
+            assert self._mig.shape == (R, R) and self._com.shape == (R, R)
+            tp = _ffi.EpiTravelPlan(R, int(plan.get("migration") is not None), int(plan.get("commute") is not None), self._mig.ctypes.data,
+                                    self._com.ctypes.data, int(plan.get("start_migration_hour", 0)), int(plan.get("end_migration_hour", 0)))
+            self.n_regions = R
+            rc = self.L.epi_create_multi(C.byref(cfg), seed, device, region, C.byref(tp), extra_capacity, C.byref(h))
         if rc:
             raise EpiError(f"epi_create failed ({rc}): {self.L.epi_last_error(None).decode()}")
         self.h = h
@@ -117,6 +128,31 @@ class Engine:
     def population(self):
         return self.L.epi_population(self.h)
 
+    @property
+    def capacity(self):
+        return self.L.epi_capacity(self.h)
+
+    # ---- traveller exchange (multi-region engines) ----
+    def travel_pack(self, hour, kind, send_ptr, capacity_records):
+        """send_ptr: device pointer (int).  Returns the per-destination record counts (host, numpy uint32[n_regions])."""
+        counts = np.zeros(self.n_regions, np.uint32)
+        self._check(self.L.epi_travel_pack(self.h, hour, kind, C.c_void_p(send_ptr), capacity_records, _ptr(counts)))
+        return counts
+
+    def travel_unpack(self, hour, kind, recv_ptr, counts_in):
+        counts_in = np.ascontiguousarray(counts_in, np.uint32)
+        self._check(self.L.epi_travel_unpack(self.h, hour, kind, C.c_void_p(recv_ptr), _ptr(counts_in)))
+
+    def finish_hour(self, hour):
+        c = EpiCounts()
+        self._check(self.L.epi_finish_hour(self.h, hour, C.byref(c)))
+        return counts_to_array(c)
+
+    def get_regions(self):
+        reg = np.zeros(self.capacity, np.uint32)
+        self._check(self.L.epi_get_regions(self.h, _ptr(reg)))
+        return reg
+
     def counts_at_start(self):
         c = EpiCounts()
         self._check(self.L.epi_counts_at_start(self.h, C.byref(c)))
@@ -138,7 +174,7 @@ class Engine:
             self._check(self.L.epi_step(self.h, hour, C.byref(c)))
         else:
             draws = np.ascontiguousarray(draws, np.uint64)
-            assert draws.shape == (self.population, _ffi.EPI_DRAWS_PER_AGENT)
+            assert draws.shape == (self.capacity, _ffi.EPI_DRAWS_PER_AGENT)
             self._check(self.L.epi_step_with_draws(self.h, hour, _ptr(draws), C.byref(c)))
         return counts_to_array(c)
 
@@ -175,7 +211,7 @@ class Engine:
         self._check(self.L.epi_expand_hospital(self.h))
 
     def get_state(self):
-        n = self.population
+        n = self.capacity
         arrs = {f: np.zeros(n, dt) for f, dt in zip(STATE_FIELDS, STATE_DTYPES)}
         self._check(self.L.epi_get_state(self.h, *[_ptr(arrs[f]) for f in STATE_FIELDS]))
         return arrs

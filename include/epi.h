@@ -76,6 +76,19 @@ typedef struct epi_intervention_event {
     int32_t status;
 } epi_intervention_event;
 
+/* common::config::TravelPlanConfig (common/src/config/travel_plan_config.rs:22-41) with regions named by their index in
+ * `regions` (== rank == GPU).  Matrices are n_regions x n_regions, row-major [from][to]. */
+typedef struct epi_travel_plan {
+    int32_t n_regions;
+    int32_t migration_enabled, commute_enabled;
+    const uint32_t* migration;
+    const uint32_t* commute;
+    uint32_t start_migration_hour, end_migration_hour;
+} epi_travel_plan;
+#define EPI_TRAVEL_RECORD_BYTES 32 /* one traveller on the wire (Commuter / Migrator, engine/src/travel) */
+#define EPI_TRAVEL_MIGRATE 0
+#define EPI_TRAVEL_COMMUTE 1
+
 typedef struct epi_engine epi_engine;
 
 /* ---- lifecycle ------------------------------------------------------------------------------------------ */
@@ -86,11 +99,19 @@ typedef struct epi_engine epi_engine;
  * index in the travel plan (0 for standalone). */
 int epi_create(const epi_config* cfg, uint64_t seed, int device, epi_engine** out);
 int epi_create_region(const epi_config* cfg, uint64_t seed, int device, int region, epi_engine** out);
+/* One region of a multi-region run (Epidemiology::new with a travel plan + EngineApp::start_with_mpi's per-rank setup,
+ * engine-app/src/main.rs:131-166): additionally applies citizen_factory::update_commuters (citizen_factory.rs:90-110),
+ * builds the house / office occupancy heaps (grid.rs:125-155, 262-277) and reserves `extra_capacity` empty agent slots
+ * for arrivals.  The engine's Philox key is `seed` (callers pass a different seed per region). */
+int epi_create_multi(const epi_config* cfg, uint64_t seed, int device, int region, const epi_travel_plan* plan, uint32_t extra_capacity,
+                     epi_engine** out);
 void epi_destroy(epi_engine* e);
 /* message of the last failed call on this handle (NULL handle: last failed epi_create / global call) */
 const char* epi_last_error(const epi_engine* e);
 /* CitizenLocationMap::current_population (allocation_map.rs:389-391) */
 uint32_t epi_population(const epi_engine* e);
+/* number of agent slots (== population for a standalone engine) */
+uint32_t epi_capacity(const epi_engine* e);
 /* counts_at_start (engine/src/utils/util.rs:45-51) */
 int epi_counts_at_start(const epi_engine* e, epi_counts* out);
 /* use the caller's CUDA stream (cudaStream_t as void*) for all subsequent work; NULL = the engine's own */
@@ -124,6 +145,27 @@ int epi_simulate_hours(epi_engine* e, uint32_t first_hour, uint32_t n_hours, int
                        int* stopped);
 /* InterventionReporter's list since epi_create / epi_reset; out may be NULL to query *n only */
 int epi_intervention_events(const epi_engine* e, epi_intervention_event* out, uint32_t max_events, uint32_t* n);
+
+/* ---- multi-region: the traveller exchange (engine/src/epidemiology_simulation.rs:391-503) -------------------------------
+ * Per exchange hour (h % 24 == 0 migrators inside the migration window, h % 24 in {7, 17} commuters) the caller runs
+ *   epi_step(hour) -> epi_travel_pack -> all-to-allv of the records (NCCL over NVLink; torch.distributed in this repo)
+ *   -> epi_travel_unpack -> epi_finish_hour.
+ * Replaces Transport::send_* / receive_* (engine/src/transport/mod.rs:34-42, mpi_transport.rs:78-215) around
+ * remove_* / assimilate_* (allocation_map.rs:165-277).  Records never leave device memory; the host sees counts and
+ * the index lists needed for the reference's sequential bookkeeping (occupancy heaps, agent slots). */
+/* Selects the leaving agents (Citizen::is_commuter / can_migrate + gen_bool(percent_outgoing), citizen/mod.rs:456-495),
+ * allots migrators to regions (EngineMigrationPlan::alloc_outgoing_to_regions, engine_migration_plan.rs:51-77), writes
+ * their records grouped by destination region into send_buf (DEVICE memory, room for capacity_records records) and
+ * removes them from the region.  counts_out[n_regions] (HOST) = records per destination. */
+int epi_travel_pack(epi_engine* e, uint32_t hour, int kind, void* send_buf, uint64_t capacity_records, uint32_t* counts_out);
+/* Installs the arrivals: recv_buf (DEVICE) holds sum(counts_in) records ordered by source region (counts_in[n_regions],
+ * HOST).  assimilate_migrators / assimilate_commuters (allocation_map.rs:214-277). */
+int epi_travel_unpack(epi_engine* e, uint32_t hour, int kind, const void* recv_buf, const uint32_t* counts_in);
+/* The tail of the multi-engine hour (epidemiology_simulation.rs:492-503): Counts after the travel adjustments,
+ * process_interventions, and stop_simulation's MultiEngine arm (:564-571, records lockdown.zero_infection_hour). */
+int epi_finish_hour(epi_engine* e, uint32_t hour, epi_counts* out);
+/* home region | work region << 8 per agent slot (0 for empty slots): Area.location_id of home_location / work_location */
+int epi_get_regions(epi_engine* e, uint32_t* reg);
 
 /* ---- interventions: the O(N) sweeps; the decisions stay with the host (interventions/ *.rs) ---------------- */
 /* CitizenLocationMap::lock_city (allocation_map.rs:349-356) */
