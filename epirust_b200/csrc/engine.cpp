@@ -276,18 +276,15 @@ void reset_travel_state(epi_engine* e) {
     e->population = e->cfg.number_of_agents;
     e->free_slots = e->free_slots0;
     if (!e->multi) return;
-    e->houses_occupancy.init(e->geo.n_houses);
-    e->offices_occupancy.init(e->geo.n_offices);
     // set_start_locations_and_occupancies (grid.rs:125-155): houses with residents and every office enter the heaps
+    std::vector<std::pair<int, int>> hxy(e->geo.n_houses), oxy(e->geo.n_offices);
+    for (uint32_t i = 0; i < e->geo.n_houses; ++i) { const uint32_t o = house_origin(e->geo, i); hxy[i] = {(int)(o & CELL_XMASK), (int)(o >> CELL_BITS)}; }
+    for (uint32_t i = 0; i < e->geo.n_offices; ++i) { const uint32_t o = office_origin(e->geo, i); oxy[i] = {(int)(o & CELL_XMASK), (int)(o >> CELL_BITS)}; }
+    e->houses_occupancy.init(hxy, 4);
+    e->offices_occupancy.init(oxy, 100);
     for (uint32_t i = 0; i < e->geo.n_houses; ++i)
-        if (e->house_count0[i] > 0) {
-            const uint32_t o = house_origin(e->geo, i);
-            e->houses_occupancy.push(i, e->house_count0[i], (int)(o & CELL_XMASK), (int)(o >> CELL_BITS));
-        }
-    for (uint32_t i = 0; i < e->geo.n_offices; ++i) {
-        const uint32_t o = office_origin(e->geo, i);
-        e->offices_occupancy.push(i, e->office_count0[i], (int)(o & CELL_XMASK), (int)(o >> CELL_BITS));
-    }
+        if (e->house_count0[i] > 0) e->houses_occupancy.push(i, e->house_count0[i]);
+    for (uint32_t i = 0; i < e->geo.n_offices; ++i) e->offices_occupancy.push(i, e->office_count0[i]);
 }
 
 void initial_counts(epi_engine* e) {

@@ -2,9 +2,9 @@
 #pragma once
 #include <cuda_runtime.h>
 
-#include <set>
+#include <algorithm>
 #include <string>
-#include <tuple>
+#include <utility>
 #include <vector>
 
 #include "../../include/epi.h"
@@ -13,38 +13,100 @@
 #include "simulation.h"
 
 namespace epi {
-// Grid::houses_occupancy / offices_occupancy (engine/src/geography/grid.rs:47-80, 279-341): pops the LEAST occupied area; ties
-// go to the greatest Area in derive(Ord) order, i.e. the greatest (start.x, start.y) (grid.rs:67-73).
+// A set of small integers with find-first: 64-ary summary tree over a bitmap.
+class RankSet {
+  public:
+    void init(size_t n) {
+        levels_.clear();
+        size_t words = (n + 63) / 64;
+        for (;;) {
+            levels_.emplace_back(words ? words : 1, 0ull);
+            if (words <= 1) break;
+            words = (words + 63) / 64;
+        }
+    }
+    void set(uint32_t i) {
+        for (auto& lv : levels_) {
+            lv[i >> 6] |= 1ull << (i & 63);
+            i >>= 6;
+        }
+    }
+    void clear(uint32_t i) {
+        for (auto& lv : levels_) {
+            lv[i >> 6] &= ~(1ull << (i & 63));
+            if (lv[i >> 6]) break;  // the summary bit above stays set
+            i >>= 6;
+        }
+    }
+    bool any() const { return levels_.back()[0] != 0; }
+    uint32_t first() const {  // precondition: any()
+        uint32_t i = 0;
+        for (size_t l = levels_.size(); l-- > 0;) i = (i << 6) | (uint32_t)__builtin_ctzll(levels_[l][i]);
+        return i;
+    }
+
+  private:
+    std::vector<std::vector<uint64_t>> levels_;
+};
+
+// Grid::houses_occupancy / offices_occupancy (engine/src/geography/grid.rs:47-80, 279-341): a priority queue that pops the
+// LEAST occupied area; ties go to the greatest Area in derive(Ord) order, i.e. the greatest (start.x, start.y)
+// (grid.rs:67-73).  Occupancies are tiny (<= 4 per house, <= 100 per office), so this is a bucket queue: one RankSet per
+// occupancy level over the areas' ranks in tie-break order -- O(1) per operation where a tree over 6 M houses costs
+// microseconds of cache misses.
 class OccupancyHeap {
   public:
-    void init(size_t n_areas) { occ_.assign(n_areas, 0); present_.assign(n_areas, 0); x_.assign(n_areas, 0); y_.assign(n_areas, 0); q_.clear(); }
-    void push(uint32_t i, uint32_t occupants, int start_x, int start_y) {
-        occ_[i] = occupants; present_[i] = 1; x_[i] = start_x; y_[i] = start_y;
-        q_.insert(key(i));
+    // start_xy[i] = (x, y) of area i's start_offset; max_level = capacity of an area
+    void init(const std::vector<std::pair<int, int>>& start_xy, uint32_t max_level) {
+        const size_t n = start_xy.size();
+        occ_.assign(n, 0);
+        present_.assign(n, 0);
+        area_of_rank_.resize(n);
+        for (size_t i = 0; i < n; ++i) area_of_rank_[i] = (uint32_t)i;
+        std::sort(area_of_rank_.begin(), area_of_rank_.end(), [&](uint32_t a, uint32_t b) { return start_xy[a] > start_xy[b]; });  // greatest first
+        rank_of_area_.resize(n);
+        for (size_t r = 0; r < n; ++r) rank_of_area_[area_of_rank_[r]] = (uint32_t)r;
+        levels_.assign(max_level + 2, RankSet());
+        for (auto& l : levels_) l.init(n);
+        lowest_ = 0;
     }
-    bool empty() const { return q_.empty(); }
-    uint32_t pop_min() {  // BinaryHeap::pop
-        auto it = q_.begin();
-        const uint32_t i = std::get<3>(*it);
-        q_.erase(it);
+    void push(uint32_t i, uint32_t occupants) {
+        occ_[i] = occupants;
+        present_[i] = 1;
+        level(occupants).set(rank_of_area_[i]);
+        lowest_ = std::min(lowest_, occupants);
+    }
+    bool empty() {
+        while (lowest_ < levels_.size() && !levels_[lowest_].any()) ++lowest_;
+        return lowest_ >= levels_.size();
+    }
+    uint32_t pop_min() {  // BinaryHeap::pop; precondition: !empty()
+        empty();
+        const uint32_t i = area_of_rank_[levels_[lowest_].first()];
+        levels_[lowest_].clear(rank_of_area_[i]);
         return i;
     }
     uint32_t occupants(uint32_t i) const { return occ_[i]; }
-    void add_occupant(uint32_t i) { occ_[i] += 1; q_.insert(key(i)); }  // add_house_occupant / add_office_occupant after a pop
-    bool remove_occupant(uint32_t i) {                                   // remove_house_occupant / remove_office_occupant
+    void add_occupant(uint32_t i) {  // add_house_occupant / add_office_occupant after a pop
+        occ_[i] += 1;
+        level(occ_[i]).set(rank_of_area_[i]);
+        lowest_ = std::min(lowest_, occ_[i]);
+    }
+    bool remove_occupant(uint32_t i) {  // remove_house_occupant / remove_office_occupant
         if (i >= present_.size() || !present_[i] || occ_[i] == 0) return false;
-        q_.erase(key(i));
+        level(occ_[i]).clear(rank_of_area_[i]);
         occ_[i] -= 1;
-        q_.insert(key(i));
+        level(occ_[i]).set(rank_of_area_[i]);
+        lowest_ = std::min(lowest_, occ_[i]);
         return true;
     }
 
   private:
-    std::tuple<uint32_t, int, int, uint32_t> key(uint32_t i) const { return {occ_[i], -x_[i], -y_[i], i}; }
-    std::set<std::tuple<uint32_t, int, int, uint32_t>> q_;
-    std::vector<uint32_t> occ_;
+    RankSet& level(uint32_t occupants) { return levels_[std::min<size_t>(occupants, levels_.size() - 1)]; }
+    std::vector<RankSet> levels_;
+    std::vector<uint32_t> occ_, area_of_rank_, rank_of_area_;
     std::vector<uint8_t> present_;
-    std::vector<int> x_, y_;
+    uint32_t lowest_ = 0;
 };
 }  // namespace epi
 
