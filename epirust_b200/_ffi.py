@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "libepirust_b200.so")
+# EPI_LIB: developer override to A/B-test an alternative build of the same CUDA library (tools_exp.py)
+LIB_PATH = os.environ.get("EPI_LIB") or os.path.join(PKG, "libepirust_b200.so")
 
 EPI_DRAWS_PER_AGENT = 16
 EPI_N_KERNEL_KINDS = 8

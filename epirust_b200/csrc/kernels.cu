@@ -39,15 +39,69 @@ enum : int { MODE_STAY = 0, MODE_WALK = 1, MODE_GOTO = 2 };
 enum : int { KIND_START = 0, KIND_MOVE = 1, KIND_END = 2 };
 
 // a load the compiler may not sink below a branch: all of an agent's words are requested in one memory round trip
+#ifndef EPI_EXP
+#define EPI_EXP 0
+#endif
 __device__ __forceinline__ uint32_t ld_early(const uint32_t* p) {
     uint32_t v;
+#if EPI_EXP & 1
+    asm volatile("ld.global.cs.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
+#else
     asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
+#endif
     return v;
 }
 __device__ __forceinline__ uint32_t ld_early_rw(const uint32_t* p) {  // for arrays this kernel also writes
     uint32_t v;
+#if EPI_EXP & 1
+    asm volatile("ld.global.cs.u32 %0, [%1];" : "=r"(v) : "l"(p));
+#else
     asm volatile("ld.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
+#endif
     return v;
+}
+__device__ __forceinline__ void st_stream(uint32_t* p, uint32_t v) {
+#if EPI_EXP & 1
+    asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+#else
+    *p = v;
+#endif
+}
+// EPI_EXP & 8: L2 policy by zone -- claims that land in the work / transport strips (random access, re-touched several
+// times per pass) are kept (evict_last), claims in the housing strip (visited in agent order) are streamed (evict_first)
+__device__ __forceinline__ uint64_t claim_policy(const Params& P, int tx) {
+    uint64_t keep, stream;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep));
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(stream));
+    return tx >= P.zone[0].sx ? keep : stream;  // zone[0] = transport strip; work and hospital lie to its right
+}
+__device__ __forceinline__ void claim_max(const Params& P, int tx, uint32_t* p, uint32_t v) {
+#if EPI_EXP & 8
+    const uint64_t pol = claim_policy(P, tx);
+    asm volatile("red.global.max.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
+#elif EPI_EXP & 2
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("red.global.max.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
+#else
+    atomicMax(p, v);
+#endif
+}
+__device__ __forceinline__ uint32_t claim_read(const Params& P, int tx, const uint32_t* p) {
+#if EPI_EXP & 8
+    const uint64_t pol = claim_policy(P, tx);
+    uint32_t v;
+    asm volatile("ld.global.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return v;
+#elif EPI_EXP & 2
+    uint64_t pol;
+    uint32_t v;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("ld.global.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return v;
+#else
+    return *p;
+#endif
 }
 
 __device__ __forceinline__ bool rect_contains(const Rect& r, int x, int y) { return r.sx <= x && r.ex >= x && r.sy <= y && r.ey >= y; }
@@ -215,7 +269,7 @@ __global__ void __launch_bounds__(256) k_hospital_scan(Params P, const uint8_t* 
 }
 
 template <int KIND, bool INJECT>
-__global__ void __launch_bounds__(256, KIND == KIND_MOVE ? 5 : 4) k_hour(Params P, DevPtrs D, uint32_t hour_offset, uint32_t h) {
+__global__ void __launch_bounds__(256, KIND == KIND_MOVE ? ((EPI_EXP & 4) ? 6 : 5) : 4) k_hour(Params P, DevPtrs D, uint32_t hour_offset, uint32_t h) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n) return;
     // one round trip: the agent's state words (and the uniform clock word)
@@ -387,7 +441,7 @@ __global__ void __launch_bounds__(256, KIND == KIND_MOVE ? 5 : 4) k_hour(Params 
     s = (s & ~(ST_STATE_MASK | (3u << ST_SEV_SHIFT) | (ST_DAY_MAX << ST_DAY_SHIFT))) | state | (sev << ST_SEV_SHIFT) | (day << ST_DAY_SHIFT);
     uint32_t prop = 0;
     if (s != s0) {
-        D.st[i] = s;
+        st_stream(D.st + i, s);
         // Counts::update_counts (counts.rs:126-140), incrementally: only an agent whose column changed touches the running
         // totals (TOT_COPIES spread copies against same-address contention); k_commit snapshots them into the hour's row.
         const uint32_t cat0 = count_category(s0), cat1 = count_category(s);
@@ -402,10 +456,10 @@ __global__ void __launch_bounds__(256, KIND == KIND_MOVE ? 5 : 4) k_hour(Params 
         prop |= PROP_MOVE | ((uint32_t)ty << CELL_BITS) | (uint32_t)tx;
         const uint32_t stamp = hour - D.clock->epoch_base + 1u;
         const uint32_t id_mask = (1u << P.id_bits) - 1u;
-        atomicMax(&D.claim[(size_t)ty * P.pitch + (size_t)tx], (stamp << P.id_bits) | (id_mask - i));
+        claim_max(P, tx, &D.claim[(size_t)ty * P.pitch + (size_t)tx], (stamp << P.id_bits) | (id_mask - i));
     }
     if (prop) prop |= (cell_byte(P, s) - 1u) << PROP_BYTE_SHIFT;
-    D.prop[i] = prop;
+    st_stream(D.prop + i, prop);
 }
 
 __global__ void __launch_bounds__(256) k_commit(Params P, DevPtrs D, uint32_t hour_offset) {
@@ -422,8 +476,8 @@ __global__ void __launch_bounds__(256) k_commit(Params P, DevPtrs D, uint32_t ho
         }
     }
     if (i >= P.n) return;
-    const uint32_t prop = D.prop[i];
-    const uint32_t c0 = D.cell[i];  // issued with the prop load: one memory round trip
+    const uint32_t prop = ld_early_rw(D.prop + i);
+    const uint32_t c0 = ld_early_rw(D.cell + i);  // issued with the prop load: one memory round trip
     if (prop == 0) return;
     const uint32_t byte = (prop >> PROP_BYTE_SHIFT) + 1u;
     const size_t at = (size_t)(c0 >> CELL_BITS) * P.pitch + (c0 & CELL_XMASK);
@@ -432,11 +486,11 @@ __global__ void __launch_bounds__(256) k_commit(Params P, DevPtrs D, uint32_t ho
         const size_t tat = (size_t)(tc >> CELL_BITS) * P.pitch + (tc & CELL_XMASK);
         const uint32_t stamp = hour - D.clock->epoch_base + 1u;
         const uint32_t id_mask = (1u << P.id_bits) - 1u;
-        const bool win = D.claim[tat] == ((stamp << P.id_bits) | (id_mask - i));  // lowest id among claimants: upcoming.entry(new).or_insert
+        const bool win = claim_read(P, (int)(tc & CELL_XMASK), D.claim + tat) == ((stamp << P.id_bits) | (id_mask - i));  // lowest id among claimants: upcoming.entry(new).or_insert
         if (win) {
             D.grid[at] = 0;
             D.grid[tat] = (uint8_t)byte;
-            D.cell[i] = tc;
+            st_stream(D.cell + i, tc);
             return;
         }
         // lost: stays at old_cell (allocation_map.rs:99-102); still refresh the byte if it changed

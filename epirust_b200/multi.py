@@ -71,8 +71,11 @@ class DistExchange:
 class MultiRegion:
     """R region engines hosted by this process (R == 1 per process under torchrun)."""
 
-    def __init__(self, engines, plan, exchange=None, max_records=1 << 17):
+    def __init__(self, engines, plan, exchange=None, max_records=1 << 17, on_outgoing=None):
+        """on_outgoing(hour, kind, send_buf, counts): called per local engine after its leavers were packed (send_buf: [n, 8] int32
+        device tensor grouped by destination; counts: numpy[n_regions]) -- the hook of Listener::outgoing_migrators_added."""
         self.engines = engines
+        self.on_outgoing = on_outgoing
         self.plan = plan
         self.kinds = exchange_hours(plan)
         self.exchange = exchange  # None: all regions are local
@@ -91,6 +94,9 @@ class MultiRegion:
         outs = []
         for e, buf in zip(self.engines, self.send):
             outs.append(e.travel_pack(hour, kind, buf.data_ptr(), self.max_records))
+            if self.on_outgoing is not None:
+                e.sync()
+                self.on_outgoing(hour, kind, buf, outs[-1])
         if self.exchange is None:
             # local all-to-allv: region r receives, in source order, what every source addressed to it
             parts = [split_records(buf, c) for buf, c in zip(self.send, outs)]
