@@ -77,9 +77,9 @@ void drain_events(epi_engine* e) {
     e->pending_events.clear();
 }
 
-size_t n_cells(const epi_engine* e) { return (size_t)e->geo.pitch * e->geo.rows; }
-// grid allocation: GRID_YPAD zero rows above and below, GRID_XPAD zero bytes before row 0 (5x5 window loads need no bounds checks)
-size_t grid_alloc_bytes(const epi_engine* e) { return (size_t)e->geo.pitch * (e->geo.rows + 2 * GRID_YPAD) + 2 * GRID_XPAD; }
+size_t n_cells(const epi_engine* e) { return (size_t)e->geo.pitch * e->geo.rows; }  // logical cells (host API)
+// grid allocation with its zero padding (layout.h); claim[] has one word per byte of it
+size_t grid_alloc_bytes(const epi_engine* e) { return e->P.grid_bytes(); }
 
 int rebuild_grid(epi_engine* e) {
     CU(cudaMemsetAsync(e->grid_alloc, 0, grid_alloc_bytes(e), e->stream));
@@ -141,7 +141,7 @@ int ensure_epoch(epi_engine* e, uint32_t first_hour, uint32_t last_hour) {
     const uint64_t limit = 1ull << (32 - e->P.id_bits);
     const bool fits = !e->claim_dirty && first_hour >= e->epoch_base && (uint64_t)(last_hour - e->epoch_base) + 1ull < limit;
     if (!fits) {
-        CU(cudaMemsetAsync(e->D.claim, 0, n_cells(e) * sizeof(uint32_t), e->stream));
+        CU(cudaMemsetAsync(e->D.claim, 0, grid_alloc_bytes(e) * sizeof(uint32_t), e->stream));
         e->epoch_base = first_hour;
         e->claim_dirty = false;
     }
@@ -384,7 +384,7 @@ int epi_create_multi(const epi_config* cfg, uint64_t seed, int device, int regio
         if (cudaSetDevice(device) != cudaSuccess) { e->err = "cudaSetDevice failed"; return fail(EPI_ERR_CUDA); }
         if (cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) != cudaSuccess) { e->err = "cudaStreamCreate failed"; return fail(EPI_ERR_CUDA); }
         e->stream = e->own_stream;
-        const size_t n = e->P.n, cells = n_cells(e);
+        const size_t n = e->P.n, cells = grid_alloc_bytes(e);
         bool ok = true;
         ok &= dev_alloc(e, &e->D.cell, n) == cudaSuccess;
         ok &= dev_alloc(e, &e->D.st, n) == cudaSuccess;
@@ -397,7 +397,7 @@ int epi_create_multi(const epi_config* cfg, uint64_t seed, int device, int regio
         ok &= dev_alloc(e, &e->i_reg, n) == cudaSuccess;
         ok &= cudaMallocHost((void**)&e->h_small, 64 * sizeof(uint32_t)) == cudaSuccess;
         ok &= dev_alloc(e, &e->grid_alloc, grid_alloc_bytes(e)) == cudaSuccess;
-        e->D.grid = e->grid_alloc ? e->grid_alloc + (size_t)e->geo.pitch * GRID_YPAD + GRID_XPAD : nullptr;
+        e->D.grid = e->grid_alloc;
         ok &= dev_alloc(e, &e->D.claim, cells) == cudaSuccess;
         ok &= dev_alloc(e, &e->D.counts, (size_t)RING_ROWS * 8) == cudaSuccess;
         ok &= dev_alloc(e, &e->D.tot, (size_t)TOT_COPIES * 8) == cudaSuccess;
@@ -636,8 +636,11 @@ int epi_get_grid(epi_engine* e, uint8_t* out, uint64_t capacity, uint32_t* pitch
     if (!out) return EPI_OK;
     if (capacity < n_cells(e)) return engine_fail(e, EPI_ERR_ARG, "epi_get_grid: buffer too small");
     CU(cudaSetDevice(e->device));
-    CU(cudaMemcpyAsync(out, e->D.grid, n_cells(e), cudaMemcpyDeviceToHost, e->stream));
+    std::vector<uint8_t> raw(grid_alloc_bytes(e));
+    CU(cudaMemcpyAsync(raw.data(), e->D.grid, raw.size(), cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
+    for (uint32_t y = 0; y < e->geo.rows; ++y)  // device layout -> row-major [rows][pitch]
+        for (uint32_t x = 0; x < e->geo.pitch; ++x) out[(size_t)y * e->geo.pitch + x] = raw[e->P.cell_offset((int)x, (int)y)];
     return EPI_OK;
 }
 

@@ -120,7 +120,7 @@ struct epi_engine {
     uint64_t seed = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     // device allocations
-    uint8_t* grid_alloc = nullptr;  // D.grid points pitch + GRID_XPAD bytes into this
+    uint8_t* grid_alloc = nullptr;  // the cell grid with its zero padding (== D.grid)
     epi::Clock* d_clock = nullptr;
     uint32_t* d_misc = nullptr;  // [0] hosp_first, [1] collisions
     uint64_t* d_draws = nullptr;

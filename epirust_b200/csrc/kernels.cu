@@ -17,9 +17,13 @@
 //
 // Claim protocol (north_star (b): lowest-agent-id priority): k_hour does atomicMax(claim[cell], stamp | ~id) -- a
 // fire-and-forget reduction, nobody waits for its result; k_commit moves the agent iff claim[cell] is its own word.
-// The hour stamp in the high bits makes clearing the claim array unnecessary.  (A three-phase variant that marks
-// CLAIMED / CONTESTED bits in the occupancy byte and touches claim[] only for contested cells was measured slower:
-// its phase-A atomic needs its return value, and the extra pass costs more than the DRAM traffic it saves.)
+// The hour stamp in the high bits makes clearing the claim array unnecessary.  Measured alternatives that lost (10 M
+// agents, B200): (1) a three-phase variant that marks CLAIMED / CONTESTED bits in the occupancy byte and touches claim[]
+// only for contested cells -- its phase-A atomic needs its return value and the extra pass costs more than the DRAM
+// traffic it saves (two agents of a house contest a cell every other hour, so "contested" is not rare); (2) atomicMax
+// with the old value returned, the displaced claimant notified through a per-agent flag so that k_commit never reads
+// claim[] -- k_commit 112 -> 90 us but k_hour 221 -> 258 us; (3) L2 evict_last / evict_first policies on the claim and
+// grid accesses by zone -- DRAM bytes unchanged (the 10 M-agent working set does not fit the L2 either way).
 //
 // Instruction budget: k_hour is issue/latency-bound before it is HBM-bound, so the agent-hour is branch-light: the
 // movement rule of the hour is reduced to (mode, rectangle) by predicated integer logic, one Philox block serves the
@@ -38,71 +42,20 @@ namespace epi {
 enum : int { MODE_STAY = 0, MODE_WALK = 1, MODE_GOTO = 2 };
 enum : int { KIND_START = 0, KIND_MOVE = 1, KIND_END = 2 };
 
-// a load the compiler may not sink below a branch: all of an agent's words are requested in one memory round trip
-#ifndef EPI_EXP
-#define EPI_EXP 0
-#endif
+// Loads the compiler may not sink below a branch: all of an agent's words are requested in one memory round trip.  The
+// per-agent arrays are streamed once per kernel, so they carry the evict-first hint (.cs) and leave the L2 to the grid and
+// the claim words, which are the randomly accessed data.
 __device__ __forceinline__ uint32_t ld_early(const uint32_t* p) {
     uint32_t v;
-#if EPI_EXP & 1
     asm volatile("ld.global.cs.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
-#else
-    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
-#endif
     return v;
 }
 __device__ __forceinline__ uint32_t ld_early_rw(const uint32_t* p) {  // for arrays this kernel also writes
     uint32_t v;
-#if EPI_EXP & 1
     asm volatile("ld.global.cs.u32 %0, [%1];" : "=r"(v) : "l"(p));
-#else
-    asm volatile("ld.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
-#endif
     return v;
 }
-__device__ __forceinline__ void st_stream(uint32_t* p, uint32_t v) {
-#if EPI_EXP & 1
-    asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-#else
-    *p = v;
-#endif
-}
-// EPI_EXP & 8: L2 policy by zone -- claims that land in the work / transport strips (random access, re-touched several
-// times per pass) are kept (evict_last), claims in the housing strip (visited in agent order) are streamed (evict_first)
-__device__ __forceinline__ uint64_t claim_policy(const Params& P, int tx) {
-    uint64_t keep, stream;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep));
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(stream));
-    return tx >= P.zone[0].sx ? keep : stream;  // zone[0] = transport strip; work and hospital lie to its right
-}
-__device__ __forceinline__ void claim_max(const Params& P, int tx, uint32_t* p, uint32_t v) {
-#if EPI_EXP & 8
-    const uint64_t pol = claim_policy(P, tx);
-    asm volatile("red.global.max.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
-#elif EPI_EXP & 2
-    uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-    asm volatile("red.global.max.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
-#else
-    atomicMax(p, v);
-#endif
-}
-__device__ __forceinline__ uint32_t claim_read(const Params& P, int tx, const uint32_t* p) {
-#if EPI_EXP & 8
-    const uint64_t pol = claim_policy(P, tx);
-    uint32_t v;
-    asm volatile("ld.global.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
-    return v;
-#elif EPI_EXP & 2
-    uint64_t pol;
-    uint32_t v;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-    asm volatile("ld.global.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
-    return v;
-#else
-    return *p;
-#endif
-}
+__device__ __forceinline__ void st_stream(uint32_t* p, uint32_t v) { asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
 __device__ __forceinline__ bool rect_contains(const Rect& r, int x, int y) { return r.sx <= x && r.ex >= x && r.sy <= y && r.ey >= y; }
 
@@ -124,11 +77,11 @@ struct Hood {
 struct Window {
     uint32_t l[5], r[5];
 };
-__device__ __forceinline__ Window load_window(const uint8_t* __restrict__ grid, uint32_t pitch, int cx, int cy) {
-    const ptrdiff_t first = (ptrdiff_t)(cy - 2) * (ptrdiff_t)pitch + (cx - 2);  // offset of the window's top-left cell
-    const uint32_t sh = (uint32_t)(first & 3) * 8u;                             // grid base and pitch are multiples of 4
-    const uint32_t* p = reinterpret_cast<const uint32_t*>(grid + (first & ~(ptrdiff_t)3));
-    const uint32_t stride = pitch >> 2;
+__device__ __forceinline__ Window load_window(const uint8_t* __restrict__ grid, const Params& P, int cx, int cy) {
+    const size_t first = P.cell_offset(cx - 2, cy - 2);  // the window's top-left cell; GRID_XOFF and pitch are multiples of 4
+    const uint32_t sh = (uint32_t)(first & 3u) * 8u;
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(grid + (first & ~(size_t)3));
+    const uint32_t stride = P.pitch >> 2;
     uint32_t a[5], b[5];
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
@@ -264,12 +217,12 @@ __global__ void __launch_bounds__(256) k_hospital_scan(Params P, const uint8_t* 
     for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < total; r += (uint64_t)gridDim.x * blockDim.x) {
         if (r >= *(volatile uint32_t*)hosp_first) return;  // ranks only grow along the stride: nothing better ahead
         const uint32_t x = (uint32_t)h.sx + (uint32_t)(r % w), y = (uint32_t)h.sy + (uint32_t)(r / w);
-        if ((grid[(size_t)y * P.pitch + x] & CELL_OCC_MASK) == 0) { atomicMin(hosp_first, (uint32_t)r); return; }
+        if ((grid[P.cell_offset((int)x, (int)y)] & CELL_OCC_MASK) == 0) { atomicMin(hosp_first, (uint32_t)r); return; }
     }
 }
 
 template <int KIND, bool INJECT>
-__global__ void __launch_bounds__(256, KIND == KIND_MOVE ? ((EPI_EXP & 4) ? 6 : 5) : 4) k_hour(Params P, DevPtrs D, uint32_t hour_offset, uint32_t h) {
+__global__ void __launch_bounds__(256, KIND == KIND_MOVE ? 6 : 4) k_hour(Params P, DevPtrs D, uint32_t hour_offset, uint32_t h) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n) return;
     // one round trip: the agent's state words (and the uniform clock word)
@@ -303,7 +256,7 @@ __global__ void __launch_bounds__(256, KIND == KIND_MOVE ? ((EPI_EXP & 4) ? 6 : 
                 } else {  // hospital full: try a random point of the own house
                     int px, py;
                     dr.point(home, px, py);
-                    if ((grid[(size_t)py * P.pitch + px] & CELL_OCC_MASK) == 0) { tx = px; ty = py; }
+                    if ((grid[P.cell_offset(px, py)] & CELL_OCC_MASK) == 0) { tx = px; ty = py; }
                 }
             }
         }
@@ -320,7 +273,7 @@ __global__ void __launch_bounds__(256, KIND == KIND_MOVE ? ((EPI_EXP & 4) ? 6 : 
         if (state == ST_R) {  // every recovered agent, every day
             int px, py;
             dr.point(home, px, py);
-            if ((grid[(size_t)py * P.pitch + px] & CELL_OCC_MASK) == 0) { tx = px; ty = py; }
+            if ((grid[P.cell_offset(px, py)] & CELL_OCC_MASK) == 0) { tx = px; ty = py; }
         }
         if (state == ST_R || state == ST_D) { s &= ~ST_HOSP; sev = 0; day = 0; }
     } else {
@@ -384,7 +337,7 @@ __global__ void __launch_bounds__(256, KIND == KIND_MOVE ? ((EPI_EXP & 4) ? 6 : 
         if (need_point) dr.point(R, bx, by);
         // second round trip: the 5x5 window around the base cell
         Window win;
-        if (mode != MODE_STAY || scan) win = load_window(grid, P.pitch, bx, by);
+        if (mode != MODE_STAY || scan) win = load_window(grid, P, bx, by);
         uint32_t pick = 0, factor = 0;
         uint64_t a = 0;
         if (mode == MODE_WALK || (dynamics && (state == ST_E || pre))) dr.common(pick, factor, a);
@@ -408,7 +361,7 @@ __global__ void __launch_bounds__(256, KIND == KIND_MOVE ? ((EPI_EXP & 4) ? 6 : 
                     // is outside the window -> second load (hours 7, 8, 16, 17 mostly)
                     Hood hd;
                     if (tx == bx + ddx && ty == by + ddy) hd = hood_at(win, ddx, ddy);
-                    else hd = hood_centre(load_window(grid, P.pitch, tx, ty));
+                    else hd = hood_centre(load_window(grid, P, tx, ty));
                     uint32_t inf = infectious_mask(hd);
                     // neighbours are clipped to the NEW current_area: R is its rectangle unless a non-working agent's
                     // area changed this hour (h = 8, 12), where R is still the old one
@@ -456,7 +409,7 @@ __global__ void __launch_bounds__(256, KIND == KIND_MOVE ? ((EPI_EXP & 4) ? 6 : 
         prop |= PROP_MOVE | ((uint32_t)ty << CELL_BITS) | (uint32_t)tx;
         const uint32_t stamp = hour - D.clock->epoch_base + 1u;
         const uint32_t id_mask = (1u << P.id_bits) - 1u;
-        claim_max(P, tx, &D.claim[(size_t)ty * P.pitch + (size_t)tx], (stamp << P.id_bits) | (id_mask - i));
+        atomicMax(&D.claim[P.cell_offset(tx, ty)], (stamp << P.id_bits) | (id_mask - i));
     }
     if (prop) prop |= (cell_byte(P, s) - 1u) << PROP_BYTE_SHIFT;
     st_stream(D.prop + i, prop);
@@ -480,13 +433,13 @@ __global__ void __launch_bounds__(256) k_commit(Params P, DevPtrs D, uint32_t ho
     const uint32_t c0 = ld_early_rw(D.cell + i);  // issued with the prop load: one memory round trip
     if (prop == 0) return;
     const uint32_t byte = (prop >> PROP_BYTE_SHIFT) + 1u;
-    const size_t at = (size_t)(c0 >> CELL_BITS) * P.pitch + (c0 & CELL_XMASK);
+    const size_t at = P.cell_offset(c0);
     if (prop & PROP_MOVE) {
         const uint32_t tc = prop & PROP_CELL_MASK;
-        const size_t tat = (size_t)(tc >> CELL_BITS) * P.pitch + (tc & CELL_XMASK);
+        const size_t tat = P.cell_offset(tc);
         const uint32_t stamp = hour - D.clock->epoch_base + 1u;
         const uint32_t id_mask = (1u << P.id_bits) - 1u;
-        const bool win = claim_read(P, (int)(tc & CELL_XMASK), D.claim + tat) == ((stamp << P.id_bits) | (id_mask - i));  // lowest id among claimants: upcoming.entry(new).or_insert
+        const bool win = D.claim[tat] == ((stamp << P.id_bits) | (id_mask - i));  // lowest id among claimants: upcoming.entry(new).or_insert
         if (win) {
             D.grid[at] = 0;
             D.grid[tat] = (uint8_t)byte;
@@ -547,8 +500,8 @@ __global__ void __launch_bounds__(256) k_build_grid(Params P, const uint32_t* __
     if (i >= P.n) return;
     if ((st[i] & ST_STATE_MASK) == ST_ABSENT) return;
     const uint32_t c = cell[i];
-    const size_t at = (size_t)(c >> CELL_BITS) * P.pitch + (c & CELL_XMASK);
-    // byte-wide check-and-set through the containing word (grid base and pitch are 4-byte aligned)
+    const size_t at = P.cell_offset(c);
+    // byte-wide check-and-set through the containing word
     uint32_t* word = (uint32_t*)(grid + (at & ~(size_t)3));
     const uint32_t shift = (uint32_t)(at & 3) * 8u;
     const uint32_t old = atomicOr(word, cell_byte(P, st[i]) << shift);

@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(256) k_travel_pack(Params P, DevPtrs D, const 
     r.st = s; r.t0 = D.t0[i]; r.home = D.home[i]; r.work = D.work[i]; r.reg = D.reg[i]; r.slot = i; r.from = (uint32_t)P.region; r.pad = 0;
     out[j] = r;
     const uint32_t c = D.cell[i];
-    D.grid[(size_t)(c >> CELL_BITS) * P.pitch + (c & CELL_XMASK)] = 0;
+    D.grid[P.cell_offset(c)] = 0;
     D.st[i] = ST_ABSENT;
     D.prop[i] = 0;
     atomicSub(D.tot + count_category(s), 1u);
@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(256) k_travel_propose(Params P, DevPtrs D, Tra
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n_in || placed[k]) return;
     const uint32_t c = arrival_cell(P, A, k, attempt);
-    if (D.grid[(size_t)(c >> CELL_BITS) * P.pitch + (c & CELL_XMASK)] != 0) return;  // occupied (also by earlier rounds' winners)
+    if (D.grid[P.cell_offset(c)] != 0) return;  // occupied (also by earlier rounds' winners)
     uint32_t slot = hash_cell(c) & table_mask;
     for (;;) {
         const uint32_t old = atomicCAS(&table_keys[slot], 0u, c + 1u);
@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(256) k_travel_grant(Params P, DevPtrs D, Trave
     if (won) {
         const uint32_t i = in_slot[k];
         D.cell[i] = c;
-        D.grid[(size_t)(c >> CELL_BITS) * P.pitch + (c & CELL_XMASK)] = (uint8_t)cell_byte(P, D.st[i]);
+        D.grid[P.cell_offset(c)] = (uint8_t)cell_byte(P, D.st[i]);
         placed[k] = 1;
     } else {
         atomicAdd(pending, 1u);

@@ -47,10 +47,12 @@ def test_config3_10m_agents_invariants_and_determinism():
         for f in STATE_FIELDS:
             assert (sa[f] == sb[f]).all(), f"same seed, different {f}"
         assert int(((sa["st"] >> 8) & 1).sum()) > 0.15 * n  # vaccinated flags were set by the sweep
-        # a different seed gives a different trajectory
+    # a different seed gives a different trajectory (the first two days' Counts can coincide: nobody leaves Exposed before hour 47)
     with Engine(cfg, seed=2) as c:
-        rows_c, _ = c.simulate_hours(1, 48)
-        assert (rows_c[:, 1:].sum(axis=1) == n).all() and (rows_c != rows_a).any()
+        rows_c, _ = c.simulate_hours(1, 72)
+        assert (rows_c[:, 1:].sum(axis=1) == n).all()
+        sc = c.get_state()
+        assert (sc["cell_x"] != sa["cell_x"]).mean() > 0.1
 
 
 def test_config5_region_20m_agents_one_day():
