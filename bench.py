@@ -197,7 +197,7 @@ def run_ours(args):
     rows = np.zeros((24 * (K + W), 7), np.uint32)
     with torch.cuda.stream(stream):
         if multi:
-            runner = MultiRegion([eng], plan, exchange=DistExchange(torch.device("cuda", local)), max_records=1 << 18)
+            runner = MultiRegion([eng], plan, exchange=DistExchange(torch.device("cuda", local)), stride_records=2 * (n // 1000) + 4096)
         simulate(1, 24 * W, rows)  # warm-up days (also builds the day graph)
         barrier()
         if rank == 0:
@@ -291,7 +291,7 @@ def run_ours(args):
             "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": wl, "agents_per_gpu": n, "grid_size": kw["grid_size"], "step": "one simulated day (24 hours)",
                        "l2": "state + grids larger than L2 (no flush needed)" if n >= 5_000_000 else "working set fits the 126 MB L2; no flush (the real run is L2-resident too)",
-                       "regions": world, "exchange": "NCCL all_to_all_single (counts, then records) at h%24 in {0, 7, 17}" if multi else "n/a", "last_counts_row": last_row},
+                       "regions": world, "exchange": "one NCCL all_to_all_single of padded segments (count in the segment header) at h%24 in {0, 7, 17}" if multi else "n/a", "last_counts_row": last_row},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)

@@ -96,7 +96,7 @@ def load():
     L.epi_capacity.argtypes = [vp]
     L.epi_capacity.restype = u32
     L.epi_travel_pack.argtypes = [vp, u32, i32, vp, u64, vp]
-    L.epi_travel_unpack.argtypes = [vp, u32, i32, vp, vp]
+    L.epi_travel_unpack.argtypes = [vp, u32, i32, vp, u64, vp]
     L.epi_finish_hour.argtypes = [vp, u32, C.POINTER(EpiCounts)]
     L.epi_get_regions.argtypes = [vp, vp]
     L.epi_destroy.argtypes = [vp]

@@ -271,20 +271,84 @@ int snapshot_initial(epi_engine* e) {
     return EPI_OK;
 }
 
-// host bookkeeping of the exchange back to its initial state
-void reset_travel_state(epi_engine* e) {
+// tie order of the occupancy heaps (grid.rs:67-73): the greatest (start.x, start.y) first -- see house_rank() in travel.cu
+uint32_t house_rank_of_index(const Geometry& g, uint32_t idx) {
+    const int hx = (int)(idx % (uint32_t)g.house_nx), hy = (int)(idx / (uint32_t)g.house_nx);
+    return (uint32_t)((g.house_nx - 1 - hx) * g.house_ny + (g.house_ny - 1 - hy));
+}
+uint32_t office_rank_of_index(const Geometry& g, uint32_t idx) {
+    const int ox = (int)(idx % (uint32_t)g.office_nx), oy = (int)(idx / (uint32_t)g.office_nx);
+    return (uint32_t)((g.office_nx - 1 - ox) * g.office_ny + (g.office_ny - 1 - oy));
+}
+
+template <class T>
+int travel_alloc(epi_engine* e, T** p, size_t count) {
+    CU(cudaMalloc((void**)p, std::max<size_t>(count, 1) * sizeof(T)));
+    e->device_bytes += count * sizeof(T);
+    e->travel_allocs.push_back((void*)*p);
+    return EPI_OK;
+}
+
+// device-side bookkeeping of the traveller exchange (multi-region engines)
+int alloc_travel(epi_engine* e, const epi_travel_plan* plan) {
+    const uint32_t R = (uint32_t)plan->n_regions, self = (uint32_t)e->P.region;
+    uint64_t most = 0;
+    for (int m = 0; m < 2; ++m) {
+        const uint32_t* mat = m == 0 ? (plan->migration_enabled ? plan->migration : nullptr) : (plan->commute_enabled ? plan->commute : nullptr);
+        if (!mat) continue;
+        uint64_t row = 0, col = 0;
+        for (uint32_t k = 0; k < R; ++k) { row += mat[(size_t)self * R + k]; col += mat[(size_t)k * R + self]; }
+        most = std::max(most, std::max(row, col));
+    }
+    epi::TravelPtrs& T = e->T;
+    T.n_regions = (int)R;
+    T.list_cap = (uint32_t)std::min<uint64_t>(2 * most + 65536, e->P.n);
+    uint32_t table = 1024;
+    while (table < 4u * T.list_cap) table <<= 1;
+    T.table_mask = table - 1u;
+    const size_t nbh = (e->geo.n_houses + 255) / 256, nbo = (e->geo.n_offices + 255) / 256;
+    int rc;
+    uint32_t* row = nullptr;
+    if ((rc = travel_alloc(e, &T.occ_house, e->geo.n_houses))) return rc;
+    if ((rc = travel_alloc(e, &T.occ_office, e->geo.n_offices))) return rc;
+    if ((rc = travel_alloc(e, &T.free_stack, e->P.n))) return rc;
+    if ((rc = travel_alloc(e, &T.tv, 1))) return rc;
+    if ((rc = travel_alloc(e, &row, R))) return rc;
+    T.plan_row = row;
+    if ((rc = travel_alloc(e, &T.list_slot, T.list_cap))) return rc;
+    if ((rc = travel_alloc(e, &T.list_dest, T.list_cap))) return rc;
+    if ((rc = travel_alloc(e, &T.list_pos, T.list_cap))) return rc;
+    if ((rc = travel_alloc(e, &T.arrivals, T.list_cap))) return rc;
+    if ((rc = travel_alloc(e, &T.arr_widx, T.list_cap))) return rc;
+    if ((rc = travel_alloc(e, &T.arr_house, T.list_cap))) return rc;
+    if ((rc = travel_alloc(e, &T.arr_office, T.list_cap))) return rc;
+    if ((rc = travel_alloc(e, &T.placed, T.list_cap))) return rc;
+    if ((rc = travel_alloc(e, &T.table_keys, table))) return rc;
+    if ((rc = travel_alloc(e, &T.table_vals, table))) return rc;
+    if ((rc = travel_alloc(e, &T.bh_house, nbh * HOUSE_CAP))) return rc;
+    if ((rc = travel_alloc(e, &T.pref_house, nbh * HOUSE_CAP))) return rc;
+    if ((rc = travel_alloc(e, &T.bh_office, nbo * OFFICE_CAP))) return rc;
+    if ((rc = travel_alloc(e, &T.pref_office, nbo * OFFICE_CAP))) return rc;
+    if ((rc = travel_alloc(e, &T.plan_house, 1))) return rc;
+    if ((rc = travel_alloc(e, &T.plan_office, 1))) return rc;
+    if ((rc = travel_alloc(e, &e->t_block_counts, (size_t)(e->P.n + 255) / 256 + 1))) return rc;
+    CU(cudaMallocHost((void**)&e->h_tv, sizeof(epi::TravelVars)));
+    CU(cudaMemsetAsync(T.tv, 0, sizeof(epi::TravelVars), e->stream));
+    CU(cudaMemcpyAsync(row, e->migration_row.data(), R * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return EPI_OK;
+}
+
+// bookkeeping of the exchange back to its initial state (set_start_locations_and_occupancies, grid.rs:125-155)
+int reset_travel_state(epi_engine* e) {
     e->population = e->cfg.number_of_agents;
-    e->free_slots = e->free_slots0;
-    if (!e->multi) return;
-    // set_start_locations_and_occupancies (grid.rs:125-155): houses with residents and every office enter the heaps
-    std::vector<std::pair<int, int>> hxy(e->geo.n_houses), oxy(e->geo.n_offices);
-    for (uint32_t i = 0; i < e->geo.n_houses; ++i) { const uint32_t o = house_origin(e->geo, i); hxy[i] = {(int)(o & CELL_XMASK), (int)(o >> CELL_BITS)}; }
-    for (uint32_t i = 0; i < e->geo.n_offices; ++i) { const uint32_t o = office_origin(e->geo, i); oxy[i] = {(int)(o & CELL_XMASK), (int)(o >> CELL_BITS)}; }
-    e->houses_occupancy.init(hxy, 4);
-    e->offices_occupancy.init(oxy, 100);
-    for (uint32_t i = 0; i < e->geo.n_houses; ++i)
-        if (e->house_count0[i] > 0) e->houses_occupancy.push(i, e->house_count0[i]);
-    for (uint32_t i = 0; i < e->geo.n_offices; ++i) e->offices_occupancy.push(i, e->office_count0[i]);
+    if (!e->multi) return EPI_OK;
+    e->n_free = (uint32_t)e->free_stack0.size();
+    CU(cudaMemcpyAsync(e->T.free_stack, e->free_stack0.data(), e->free_stack0.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemcpyAsync(e->T.occ_house, e->occ_house0.data(), e->occ_house0.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemcpyAsync(e->T.occ_office, e->occ_office0.data(), e->occ_office0.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return EPI_OK;
 }
 
 void initial_counts(epi_engine* e) {
@@ -363,24 +427,28 @@ int epi_create_multi(const epi_config* cfg, uint64_t seed, int device, int regio
                 e->commute_row.assign(plan->commute + (size_t)region * R, plan->commute + (size_t)(region + 1) * R);
                 apply_commute_plan(agents, n_agents, region, e->commute_row);
             }
-            e->house_count0.assign(e->geo.n_houses, 0);
-            e->office_count0.assign(e->geo.n_offices, 0);
+            // houses that have residents enter the heap with their resident count; every office enters with its number of
+            // workers whose work region is this one (grid.rs:125-155, 262-277).  Stored in tie order.
+            e->occ_house0.assign(e->geo.n_houses, 0);
+            e->occ_office0.assign(e->geo.n_offices, 0);
             for (uint32_t i = 0; i < n_agents; ++i) {
-                e->house_count0[house_index_of(e->geo, agents.home[i])]++;
+                e->occ_house0[house_rank_of_index(e->geo, house_index_of(e->geo, agents.home[i]))]++;
                 const bool working = ((agents.st[i] >> ST_WS_SHIFT) & 3u) != WS_NA;
-                if (working && ((agents.reg[i] >> 8) & 0xFFu) == (uint32_t)region) e->office_count0[office_index_of(e->geo, agents.work[i])]++;
+                if (working && ((agents.reg[i] >> 8) & 0xFFu) == (uint32_t)region) e->occ_office0[office_rank_of_index(e->geo, office_index_of(e->geo, agents.work[i]))]++;
             }
+            for (uint32_t& v : e->occ_house0)
+                if (v == 0) v = OCC_ABSENT;
         }
         // empty slots for arrivals
         agents.resize(capacity);
         for (uint32_t i = n_agents; i < capacity; ++i) { agents.st[i] = ST_ABSENT; agents.cell[i] = agents.t0[i] = agents.home[i] = agents.work[i] = agents.wsa[i] = agents.reg[i] = 0; }
-        e->free_slots0.clear();
-        for (uint32_t sl = capacity; sl-- > n_agents;) e->free_slots0.push_back(sl);  // pop order: n, n+1, ...
+        e->free_stack0.clear();
+        for (uint32_t sl = capacity; sl-- > n_agents;) e->free_stack0.push_back(sl);  // pop order: n, n+1, ...
         e->P.n = capacity;
         uint32_t bits = 1;
         while ((1ull << bits) < (uint64_t)capacity) ++bits;
         e->P.id_bits = bits;
-        reset_travel_state(e);
+        e->population = n_agents;
         if (cudaSetDevice(device) != cudaSuccess) { e->err = "cudaSetDevice failed"; return fail(EPI_ERR_CUDA); }
         if (cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) != cudaSuccess) { e->err = "cudaStreamCreate failed"; return fail(EPI_ERR_CUDA); }
         e->stream = e->own_stream;
@@ -414,7 +482,14 @@ int epi_create_multi(const epi_config* cfg, uint64_t seed, int device, int regio
         e->D.hosp_first = e->d_misc;
         e->D.clock = e->d_clock;
         e->D.draws = nullptr;
-        int rc = upload_agents(e, agents);
+        int rc = EPI_OK;
+        if (plan) {
+            rc = alloc_travel(e, plan);
+            if (rc) return fail(rc);
+            rc = reset_travel_state(e);
+            if (rc) return fail(rc);
+        }
+        rc = upload_agents(e, agents);
         if (rc) return fail(rc);
         rc = snapshot_initial(e);
         if (rc) return fail(rc);
@@ -436,9 +511,10 @@ void epi_destroy(epi_engine* e) {
     drop_graph(e);
     for (auto& pe : e->pending_events) { cudaEventDestroy(pe.second.first); cudaEventDestroy(pe.second.second); }
     void* ptrs[] = {e->D.cell, e->D.st, e->D.t0, e->D.home, e->D.work, e->D.wsa, e->D.prop, e->grid_alloc, e->D.claim, e->D.counts, e->D.tot,
-                    e->d_clock, e->d_misc, e->d_draws, e->i_cell, e->i_st, e->i_t0, e->i_home, e->i_work, e->i_wsa, e->D.reg, e->i_reg,
-                    e->t_block_counts, e->t_total, e->t_out_slots, e->t_out_dest, e->t_idx, e->t_table_keys, e->t_table_vals, e->t_placed};
+                    e->d_clock, e->d_misc, e->d_draws, e->i_cell, e->i_st, e->i_t0, e->i_home, e->i_work, e->i_wsa, e->D.reg, e->i_reg};
     for (void* p : ptrs) if (p) cudaFree(p);
+    for (void* p : e->travel_allocs) cudaFree(p);
+    if (e->h_tv) cudaFreeHost(e->h_tv);
     if (e->h_counts) cudaFreeHost(e->h_counts);
     if (e->h_small) cudaFreeHost(e->h_small);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
@@ -484,7 +560,10 @@ int epi_reset(epi_engine* e) {
     CU(cudaMemcpyAsync(e->D.wsa, e->i_wsa, nb, cudaMemcpyDeviceToDevice, e->stream));
     CU(cudaMemcpyAsync(e->D.reg, e->i_reg, nb, cudaMemcpyDeviceToDevice, e->stream));
     CU(cudaMemsetAsync(e->D.prop, 0, nb, e->stream));
-    reset_travel_state(e);
+    {
+        const int rc = reset_travel_state(e);
+        if (rc) return rc;
+    }
     if (e->P.hospital_gen != 0) { e->P.hospital_gen = 0; drop_graph(e); }
     initial_counts(e);
     e->interventions = epi::Interventions(e->cfg);

@@ -12,104 +12,6 @@
 #include "layout.h"
 #include "simulation.h"
 
-namespace epi {
-// A set of small integers with find-first: 64-ary summary tree over a bitmap.
-class RankSet {
-  public:
-    void init(size_t n) {
-        levels_.clear();
-        size_t words = (n + 63) / 64;
-        for (;;) {
-            levels_.emplace_back(words ? words : 1, 0ull);
-            if (words <= 1) break;
-            words = (words + 63) / 64;
-        }
-    }
-    void set(uint32_t i) {
-        for (auto& lv : levels_) {
-            lv[i >> 6] |= 1ull << (i & 63);
-            i >>= 6;
-        }
-    }
-    void clear(uint32_t i) {
-        for (auto& lv : levels_) {
-            lv[i >> 6] &= ~(1ull << (i & 63));
-            if (lv[i >> 6]) break;  // the summary bit above stays set
-            i >>= 6;
-        }
-    }
-    bool any() const { return levels_.back()[0] != 0; }
-    uint32_t first() const {  // precondition: any()
-        uint32_t i = 0;
-        for (size_t l = levels_.size(); l-- > 0;) i = (i << 6) | (uint32_t)__builtin_ctzll(levels_[l][i]);
-        return i;
-    }
-
-  private:
-    std::vector<std::vector<uint64_t>> levels_;
-};
-
-// Grid::houses_occupancy / offices_occupancy (engine/src/geography/grid.rs:47-80, 279-341): a priority queue that pops the
-// LEAST occupied area; ties go to the greatest Area in derive(Ord) order, i.e. the greatest (start.x, start.y)
-// (grid.rs:67-73).  Occupancies are tiny (<= 4 per house, <= 100 per office), so this is a bucket queue: one RankSet per
-// occupancy level over the areas' ranks in tie-break order -- O(1) per operation where a tree over 6 M houses costs
-// microseconds of cache misses.
-class OccupancyHeap {
-  public:
-    // start_xy[i] = (x, y) of area i's start_offset; max_level = capacity of an area
-    void init(const std::vector<std::pair<int, int>>& start_xy, uint32_t max_level) {
-        const size_t n = start_xy.size();
-        occ_.assign(n, 0);
-        present_.assign(n, 0);
-        area_of_rank_.resize(n);
-        for (size_t i = 0; i < n; ++i) area_of_rank_[i] = (uint32_t)i;
-        std::sort(area_of_rank_.begin(), area_of_rank_.end(), [&](uint32_t a, uint32_t b) { return start_xy[a] > start_xy[b]; });  // greatest first
-        rank_of_area_.resize(n);
-        for (size_t r = 0; r < n; ++r) rank_of_area_[area_of_rank_[r]] = (uint32_t)r;
-        levels_.assign(max_level + 2, RankSet());
-        for (auto& l : levels_) l.init(n);
-        lowest_ = 0;
-    }
-    void push(uint32_t i, uint32_t occupants) {
-        occ_[i] = occupants;
-        present_[i] = 1;
-        level(occupants).set(rank_of_area_[i]);
-        lowest_ = std::min(lowest_, occupants);
-    }
-    bool empty() {
-        while (lowest_ < levels_.size() && !levels_[lowest_].any()) ++lowest_;
-        return lowest_ >= levels_.size();
-    }
-    uint32_t pop_min() {  // BinaryHeap::pop; precondition: !empty()
-        empty();
-        const uint32_t i = area_of_rank_[levels_[lowest_].first()];
-        levels_[lowest_].clear(rank_of_area_[i]);
-        return i;
-    }
-    uint32_t occupants(uint32_t i) const { return occ_[i]; }
-    void add_occupant(uint32_t i) {  // add_house_occupant / add_office_occupant after a pop
-        occ_[i] += 1;
-        level(occ_[i]).set(rank_of_area_[i]);
-        lowest_ = std::min(lowest_, occ_[i]);
-    }
-    bool remove_occupant(uint32_t i) {  // remove_house_occupant / remove_office_occupant
-        if (i >= present_.size() || !present_[i] || occ_[i] == 0) return false;
-        level(occ_[i]).clear(rank_of_area_[i]);
-        occ_[i] -= 1;
-        level(occ_[i]).set(rank_of_area_[i]);
-        lowest_ = std::min(lowest_, occ_[i]);
-        return true;
-    }
-
-  private:
-    RankSet& level(uint32_t occupants) { return levels_[std::min<size_t>(occupants, levels_.size() - 1)]; }
-    std::vector<RankSet> levels_;
-    std::vector<uint32_t> occ_, area_of_rank_, rank_of_area_;
-    std::vector<uint8_t> present_;
-    uint32_t lowest_ = 0;
-};
-}  // namespace epi
-
 struct epi_engine {
     explicit epi_engine(const epi_config& c) : cfg(c), interventions(c) {}
     epi_config cfg{};
@@ -149,16 +51,17 @@ struct epi_engine {
     bool migration_enabled = false, commute_enabled = false;
     std::vector<uint32_t> migration_row, commute_row;  // [to]
     uint32_t start_migration_hour = 0, end_migration_hour = 0;
-    std::vector<uint32_t> free_slots, free_slots0;     // LIFO: arrivals pop, departures push
-    epi::OccupancyHeap houses_occupancy, offices_occupancy;
-    std::vector<uint32_t> house_count0, office_count0;  // initial occupancies (epi_reset)
+    // The reference's sequential bookkeeping of the exchange lives on the device (travel.cu): the free-slot stack (LIFO: arrivals
+    // pop, departures push) and the house / office occupancy heaps (grid.rs:47-80, 279-341) as occupancy arrays in tie order.
+    // The host keeps the stack height and the initial images for epi_reset.
+    uint32_t n_free = 0;
+    std::vector<uint32_t> free_stack0, occ_house0, occ_office0;
     uint32_t* i_reg = nullptr;
-    // travel scratch on the device
-    uint32_t *t_block_counts = nullptr, *t_total = nullptr, *t_out_slots = nullptr, *t_out_dest = nullptr, *t_idx = nullptr;
-    uint32_t *t_table_keys = nullptr, *t_table_vals = nullptr;
-    uint8_t* t_placed = nullptr;
-    size_t t_list_capacity = 0, t_table_capacity = 0;
-    uint32_t* h_small = nullptr;  // pinned, 64 words
+    epi::TravelPtrs T{};
+    uint32_t* t_block_counts = nullptr;
+    std::vector<void*> travel_allocs;  // everything T points to (freed by epi_destroy)
+    epi::TravelVars* h_tv = nullptr;   // pinned mirror of T.tv
+    uint32_t* h_small = nullptr;       // pinned, 64 words
     epi_counts last_counts{};
     bool have_last_row = false;  // last_counts is the row of the hour just before the next one to run
     // host side of CitizenLocationMap::process_interventions (allocation_map.rs:306-337): the decisions

@@ -104,6 +104,7 @@ Params make_params(const epi_config& c, const Geometry& g, uint64_t seed, int re
     P.work = g.work;
     P.hospital_gen = 0;
     P.house_nx = g.house_nx; P.office_nx = g.office_nx;
+    P.house_ny = g.house_ny; P.office_ny = g.office_ny;
     P.regular_start = c.regular_transmission_start_day;
     P.high_start = c.high_transmission_start_day;
     P.last_day = c.last_day;

@@ -15,12 +15,11 @@ void launch_lock(const Params& P, const DevPtrs& D, cudaStream_t s);
 void launch_unlock(const Params& P, const DevPtrs& D, cudaStream_t s);
 void launch_vaccinate(const Params& P, const DevPtrs& D, uint64_t thr, uint32_t hour, cudaStream_t s);
 void launch_build_grid(const Params& P, const DevPtrs& D, uint32_t* collisions, cudaStream_t s);
-// travel.cu
-void launch_travel_select(const Params& P, const DevPtrs& D, const TravelArgs& A, uint32_t* block_counts, uint32_t* total, uint32_t* out_slots,
-                          uint32_t* out_dest, int phase, cudaStream_t s);
-void launch_travel_pack(const Params& P, const DevPtrs& D, const uint32_t* send_slots, uint32_t n_send, TravelRecord* out, cudaStream_t s);
-void launch_travel_install(const Params& P, const DevPtrs& D, const TravelArgs& A, const TravelRecord* in, uint32_t n_in, const uint32_t* in_slot,
-                           const uint32_t* in_home, const uint32_t* in_work, cudaStream_t s);
-void launch_travel_round(const Params& P, const DevPtrs& D, const TravelArgs& A, uint32_t n_in, uint32_t attempt, uint8_t* placed, const uint32_t* in_slot,
-                         uint32_t* table_keys, uint32_t* table_vals, uint32_t table_mask, uint32_t* pending, cudaStream_t s);
+// travel.cu (each returns the number of kernels it launched)
+unsigned launch_travel_leave(const Params& P, const DevPtrs& D, const TravelArgs& A, const TravelPtrs& T, uint32_t* block_counts, TravelRecord* send,
+                             uint32_t stride, uint32_t free_top, cudaStream_t s);
+unsigned launch_travel_arrive(const Params& P, const DevPtrs& D, const TravelArgs& A, const TravelPtrs& T, const TravelRecord* recv, uint32_t stride,
+                              uint32_t n_in, uint32_t max_segment, uint32_t n_houses, uint32_t n_offices, uint32_t free_top, cudaStream_t s);
+unsigned launch_travel_rounds(const Params& P, const DevPtrs& D, const TravelArgs& A, const TravelPtrs& T, uint32_t n_in, uint32_t first_attempt, uint32_t n_rounds,
+                              uint32_t free_top, cudaStream_t s);
 }  // namespace epi

@@ -83,6 +83,7 @@ struct Params {
     Rect work;         // the work strip (offices live here)
     int hospital_gen;  // which hospital rectangle is grid.hospital_area now: zone[2 + hospital_gen]
     int house_nx, office_nx;        // houses / offices per row (area_factory, geography/area.rs:95-117)
+    int house_ny, office_ny;        // rows of houses / offices
     // disease (common/src/disease/mod.rs:26-45)
     uint32_t regular_start, high_start, last_day;
     uint32_t exposed_duration, pre_symptomatic_duration;
@@ -119,6 +120,47 @@ struct TravelArgs {
     int kind;               // TRAVEL_MIGRATE (h % 24 == 0) or TRAVEL_COMMUTE (h % 24 in {7, 17})
     uint32_t hour, hour_of_day;
     uint64_t thr_outgoing;  // Bernoulli threshold of EngineMigrationPlan::percent_outgoing
+};
+
+// ---- traveller exchange: device-resident bookkeeping (travel.cu) ------------------------------------------------------------
+constexpr uint32_t TRAVEL_MAX_REGIONS = 256;
+constexpr uint32_t OCC_ABSENT = 0xFFFFFFFFu;  // a house / office that is not in the occupancy heap (grid.rs:125-155: houses without residents)
+constexpr uint32_t HOUSE_CAP = 4, OFFICE_CAP = 100;  // HOME_SIZE^2, OFFICE_SIZE^2 (constants.rs:45-46)
+enum : uint32_t {
+    TERR_LIST_OVERFLOW = 1, TERR_SEGMENT_OVERFLOW = 2, TERR_NO_HOUSE = 4, TERR_NO_OFFICE = 8, TERR_HOUSES_FULL = 16, TERR_OFFICES_FULL = 32,
+    TERR_BAD_REGION = 64,
+};
+// scalars of one exchange; the host reads them back once per pack / unpack
+struct TravelVars {
+    uint32_t total;      // leaving candidates, in ascending slot order
+    uint32_t n_send;     // records written to the send buffer
+    uint32_t n_working;  // arriving migrators that take an office
+    uint32_t pending;    // arrivals still without a cell after the placement rounds so far
+    uint32_t err;        // TERR_* flags
+    uint32_t pad[3];
+    uint32_t cnt[TRAVEL_MAX_REGIONS];   // records per destination region
+    uint32_t base[TRAVEL_MAX_REGIONS];  // exclusive prefix of cnt
+};
+// the pop sequence of an occupancy heap for K arrivals ("water filling"), see travel.cu
+struct FillPlan {
+    uint32_t K, L, l_last, last_count;  // K pops; lowest non-empty level; level of the last pop; pops on that last level
+    uint32_t start[OFFICE_CAP + 1];     // start[l] = index of the first pop that is served from level l
+};
+struct TravelPtrs {
+    uint32_t *occ_house, *occ_office;  // occupants per house / office in heap tie-break order (rank), OCC_ABSENT = not in the heap
+    uint32_t* free_stack;              // free agent slots, LIFO: arrivals pop from the top, departures push
+    TravelVars* tv;
+    const uint32_t* plan_row;          // this region's row of the migration matrix [n_regions]
+    uint32_t *list_slot, *list_dest, *list_pos;  // leaving candidates (ascending slot), their destination, their index inside the destination's segment
+    TravelRecord* arrivals;            // received records, contiguous, ordered by source region
+    uint32_t *arr_widx, *arr_house, *arr_office;  // per arrival: rank among working arrivals, assigned house / office (rank order index)
+    uint8_t* placed;
+    uint32_t *table_keys, *table_vals;  // placement round hash table
+    uint32_t table_mask;
+    uint32_t list_cap;
+    uint32_t *bh_house, *pref_house, *bh_office, *pref_office;  // per-block occupancy histograms and per-level block prefixes
+    FillPlan *plan_house, *plan_office;
+    int n_regions;
 };
 
 struct Clock {           // device-resident so CUDA graphs can be replayed for any day

@@ -1,13 +1,27 @@
 // sm_100a kernels of the daily traveller exchange (north_star: "packs and unpacks migrating agents on device").
-// Replaces the per-agent parts of CitizenLocationMap::simulate's traveller selection (allocation_map.rs:104-120),
-// remove_migrators / remove_commuters (:165-212) and assimilate_migrators / assimilate_commuters (:214-277).
-// The payload goes GPU -> GPU (NCCL all-to-allv over NVLink, driven by the caller); the host only sees counts and the
-// small index lists it needs for the reference's sequential bookkeeping (occupancy heaps, free slots).
+// Replaces CitizenLocationMap::simulate's traveller selection (allocation_map.rs:104-120), remove_migrators /
+// remove_commuters (:165-212), assimilate_migrators / assimilate_commuters (:214-277), the allotment of migrators to regions
+// (engine_migration_plan.rs:51-77, migrators_by_engine.rs:34-55), commuters_by_region.rs:59-78 and the house / office
+// occupancy heaps (grid.rs:47-80, 279-341).  Everything the reference does sequentially on the host is done here on the
+// device with the same result; the host only learns the per-region record counts (it needs them for the collective).
 //
-//   k_travel_flag_count / k_travel_scan / k_travel_scatter   ordered stream compaction of the leaving agents (ascending slot)
-//   k_travel_pack        records -> send buffer (grouped by destination), agents removed from the region
-//   k_travel_install     arrivals -> agent slots (Citizen::from_migrator / from_commuter, citizen/mod.rs:113-154)
-//   k_travel_propose / k_travel_grant   placement rounds: distinct vacant cells of the arrival strip, lowest arrival index wins
+// Leaving (epi_travel_pack):
+//   k_travel_flag_count / k_travel_scan / k_travel_scatter   ordered compaction of the leaving candidates (ascending slot)
+//   k_travel_plan      records per destination: migrators by position in the list (floor(share * total) from the front,
+//                      the surplus stays), commuters by their work / home region; segment headers
+//   k_travel_rank      commuters: stable index inside the destination's segment
+//   k_travel_pack      record -> segment of the destination; the agent leaves: cell vacated, slot pushed on the free stack,
+//                      Counts decremented, its house / office lose an occupant (migrators)
+// Arriving (epi_travel_unpack):
+//   k_travel_gather    segments (one per source region) -> contiguous arrival list, ordered by source region
+//   k_travel_wscan     rank of every arriving migrator among the working ones (they also take an office)
+//   k_occ_*            "water filling": the pop sequence of the reference's BinaryHeap of areas for K arrivals, in parallel.
+//                      The heap pops the least occupied area, ties to the greatest (start.x, start.y); a popped area
+//                      returns with one more occupant.  So the pops run level by level: first every area of the lowest
+//                      occupancy L in tie order, then every area whose occupancy was <= L + 1 in tie order, and so on.
+//                      occ[] is stored in tie order, so "the q-th area with occupancy <= l" is a prefix count.
+//   k_travel_install   arrival k -> the k-th slot from the top of the free stack (Citizen::from_migrator / from_commuter)
+//   k_travel_propose / k_travel_grant   placement rounds: distinct vacant cells of the arrival strip, lowest arrival wins
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -25,7 +39,7 @@ __device__ __forceinline__ bool can_move_word(uint32_t s) {
     return !(symptomatic || (s & (ST_HOSP | ST_ISO)) || state == ST_D);
 }
 
-// 0 = stays; otherwise destination region + 1 (commuters) or 1 (migrator candidate; the host allots destinations)
+// 0 = stays; otherwise destination region + 1 (commuters) or 1 (migrator candidate; k_travel_plan allots destinations)
 __device__ __forceinline__ uint32_t travel_flag(const Params& P, const TravelArgs& A, uint32_t i, uint32_t s, uint32_t reg) {
     if ((s & ST_STATE_MASK) == ST_ABSENT || !can_move_word(s)) return 0;
     const uint32_t home_reg = reg & 0xFFu, work_reg = (reg >> 8) & 0xFFu, self = (uint32_t)P.region;
@@ -38,6 +52,51 @@ __device__ __forceinline__ uint32_t travel_flag(const Params& P, const TravelArg
     return bernoulli(philox_draw(P.seed, i, A.hour, DOM_MIGRATE, 0), A.thr_outgoing) ? 1u : 0u;
 }
 
+// tie order of the occupancy heaps: greatest (start.x, start.y) first (grid.rs:67-73)
+__device__ __forceinline__ uint32_t house_rank(const Params& P, uint32_t origin) {
+    const int hx = ((int)(origin & CELL_XMASK) - P.housing().sx) / 2, hy = ((int)((origin >> CELL_BITS) & CELL_XMASK) - P.housing().sy) / 2;
+    return (uint32_t)((P.house_nx - 1 - hx) * P.house_ny + (P.house_ny - 1 - hy));
+}
+__device__ __forceinline__ uint32_t house_origin_of_rank(const Params& P, uint32_t rank) {
+    const int hx = P.house_nx - 1 - (int)(rank / (uint32_t)P.house_ny), hy = P.house_ny - 1 - (int)(rank % (uint32_t)P.house_ny);
+    return ((uint32_t)(P.housing().sy + 2 * hy) << CELL_BITS) | (uint32_t)(P.housing().sx + 2 * hx);
+}
+__device__ __forceinline__ uint32_t office_rank(const Params& P, uint32_t origin) {
+    const int ox = ((int)(origin & CELL_XMASK) - P.work.sx) / 10, oy = ((int)((origin >> CELL_BITS) & CELL_XMASK) - P.work.sy) / 10;
+    return (uint32_t)((P.office_nx - 1 - ox) * P.office_ny + (P.office_ny - 1 - oy));
+}
+__device__ __forceinline__ uint32_t office_origin_of_rank(const Params& P, uint32_t rank) {
+    const int ox = P.office_nx - 1 - (int)(rank / (uint32_t)P.office_ny), oy = P.office_ny - 1 - (int)(rank % (uint32_t)P.office_ny);
+    return ((uint32_t)(P.work.sy + 10 * oy) << CELL_BITS) | (uint32_t)(P.work.sx + 10 * ox);
+}
+
+// exclusive prefix of `v` over the block (blockDim.x <= 1024, multiple of 32); *block_total receives the sum
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* warp_sums, uint32_t* block_total) {
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+        if ((int)lane >= o) x += y;
+    }
+    __syncthreads();  // warp_sums may still be read by the previous call
+    if (lane == 31) warp_sums[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = lane < n_warps ? warp_sums[lane] : 0u;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, w, o);
+            if ((int)lane >= o) w += y;
+        }
+        warp_sums[lane] = w;  // inclusive prefix of the warp sums
+    }
+    __syncthreads();
+    *block_total = warp_sums[n_warps - 1];
+    return x - v + (warp ? warp_sums[warp - 1] : 0u);
+}
+
+// ---- leaving ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_travel_flag_count(Params P, DevPtrs D, TravelArgs A, uint32_t* __restrict__ block_counts) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t f = i < P.n ? travel_flag(P, A, i, D.st[i], D.reg[i]) : 0u;
@@ -45,45 +104,25 @@ __global__ void __launch_bounds__(256) k_travel_flag_count(Params P, DevPtrs D, 
     if (threadIdx.x == 0) block_counts[blockIdx.x] = (uint32_t)n;
 }
 
-// exclusive scan of the block counts by ONE block (the lists are short; this is launched 3 times per simulated day)
-__global__ void __launch_bounds__(1024) k_travel_scan(uint32_t* __restrict__ block_counts, uint32_t n_blocks, uint32_t* __restrict__ total_out) {
+// exclusive scan of the block counts by ONE block (launched 3 times per simulated day)
+__global__ void __launch_bounds__(1024) k_travel_scan(uint32_t* __restrict__ block_counts, uint32_t n_blocks, TravelVars* __restrict__ tv) {
     __shared__ uint32_t warp_sums[32];
-    __shared__ uint32_t carry;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
-    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t carry = 0;
     for (uint32_t base = 0; base < n_blocks; base += 1024u) {
         const uint32_t idx = base + threadIdx.x;
         const uint32_t v = idx < n_blocks ? block_counts[idx] : 0u;
-        uint32_t x = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
-            if ((int)lane >= o) x += y;
-        }
-        if (lane == 31) warp_sums[warp] = x;
-        __syncthreads();
-        if (warp == 0) {
-            uint32_t w = warp_sums[lane];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, w, o);
-                if ((int)lane >= o) w += y;
-            }
-            warp_sums[lane] = w;
-        }
-        __syncthreads();
-        const uint32_t incl = x + (warp ? warp_sums[warp - 1] : 0u) + carry;
-        if (idx < n_blocks) block_counts[idx] = incl - v;  // exclusive prefix
-        __syncthreads();
-        if (threadIdx.x == 1023) carry = incl;
-        __syncthreads();
+        uint32_t total;
+        const uint32_t ex = block_exclusive_scan(v, warp_sums, &total);
+        if (idx < n_blocks) block_counts[idx] = carry + ex;
+        carry += total;
     }
-    if (threadIdx.x == 0) *total_out = carry;
+    if (threadIdx.x == 0) {
+        tv->total = carry;
+        tv->n_send = 0; tv->n_working = 0; tv->pending = 0;
+    }
 }
 
-__global__ void __launch_bounds__(256) k_travel_scatter(Params P, DevPtrs D, TravelArgs A, const uint32_t* __restrict__ block_offsets,
-                                                         uint32_t* __restrict__ out_slots, uint32_t* __restrict__ out_dest) {
+__global__ void __launch_bounds__(256) k_travel_scatter(Params P, DevPtrs D, TravelArgs A, TravelPtrs T, const uint32_t* __restrict__ block_offsets) {
     __shared__ uint32_t warp_counts[8];
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t f = i < P.n ? travel_flag(P, A, i, D.st[i], D.reg[i]) : 0u;
@@ -95,38 +134,261 @@ __global__ void __launch_bounds__(256) k_travel_scatter(Params P, DevPtrs D, Tra
         uint32_t rank = __popc(b & ((1u << lane) - 1u));
         for (unsigned w = 0; w < warp; ++w) rank += warp_counts[w];
         const uint32_t at = block_offsets[blockIdx.x] + rank;
-        out_slots[at] = i;
-        out_dest[at] = f - 1u;
+        if (at < T.list_cap) {
+            T.list_slot[at] = i;
+            T.list_dest[at] = f - 1u;
+        } else atomicOr(&T.tv->err, TERR_LIST_OVERFLOW);
     }
 }
 
-// send_slots[j] (already grouped by destination by the host) -> record j; the agent leaves: cell vacated, slot emptied,
-// Counts decremented (decrement_counts, allocation_map.rs:291-301)
-__global__ void __launch_bounds__(256) k_travel_pack(Params P, DevPtrs D, const uint32_t* __restrict__ send_slots, uint32_t n_send, TravelRecord* __restrict__ out) {
-    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n_send) return;
-    const uint32_t i = send_slots[j];
+// Records per destination and the segment headers.  Migrators: EngineMigrationPlan::alloc_outgoing_to_regions
+// (engine_migration_plan.rs:51-77) + MigratorsByRegion::alloc_citizens (migrators_by_engine.rs:34-55): regions in plan
+// order take floor(share * total) from the front of the list, the rest stays.  Commuters:
+// CommutersByRegion::get_commuters_by_region (commuters_by_region.rs:59-78).
+__global__ void __launch_bounds__(1024) k_travel_plan(Params P, TravelArgs A, TravelPtrs T, TravelRecord* __restrict__ send, uint32_t stride) {
+    __shared__ uint32_t hist[TRAVEL_MAX_REGIONS];
+    TravelVars* tv = T.tv;
+    const uint32_t R = (uint32_t)T.n_regions;
+    const uint32_t total = min(tv->total, T.list_cap);
+    for (uint32_t r = threadIdx.x; r < TRAVEL_MAX_REGIONS; r += blockDim.x) hist[r] = 0;
+    __syncthreads();
+    if (A.kind == TRAVEL_COMMUTE) {
+        for (uint32_t p = threadIdx.x; p < total; p += blockDim.x) {
+            const uint32_t d = T.list_dest[p];
+            if (d < R) atomicAdd(&hist[d], 1u);
+            else atomicOr(&tv->err, TERR_BAD_REGION);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        uint32_t front = 0;
+        if (A.kind == TRAVEL_MIGRATE) {
+            uint64_t planned_total = 0;
+            for (uint32_t to = 0; to < R; ++to) planned_total += T.plan_row[to];
+            for (uint32_t to = 0; to < R; ++to) {
+                uint32_t count = 0;
+                if ((int)to != P.region && T.plan_row[to] != 0) {
+                    const double share = (double)T.plan_row[to] / (double)planned_total;
+                    count = (uint32_t)(int32_t)(share * (double)(int32_t)total);
+                    if (count > total - front) count = total - front;
+                }
+                tv->cnt[to] = count; tv->base[to] = front;
+                front += count;
+            }
+        } else {
+            for (uint32_t to = 0; to < R; ++to) { tv->cnt[to] = hist[to]; tv->base[to] = front; front += hist[to]; }
+        }
+        tv->n_send = front;
+    }
+    __syncthreads();
+    for (uint32_t to = threadIdx.x; to < R; to += blockDim.x) {
+        if (tv->cnt[to] + 1u > stride) atomicOr(&tv->err, TERR_SEGMENT_OVERFLOW);
+        TravelRecord h{};
+        h.st = min(tv->cnt[to], stride - 1u);  // header: records in this segment
+        h.from = (uint32_t)P.region;
+        send[(size_t)to * stride] = h;
+    }
+}
+
+// commuters: list_pos[p] = number of earlier candidates with the same destination (block d serves destination d)
+__global__ void __launch_bounds__(1024) k_travel_rank(TravelPtrs T) {
+    __shared__ uint32_t warp_sums[32];
+    const uint32_t d = blockIdx.x, total = min(T.tv->total, T.list_cap);
+    uint32_t carry = 0;
+    for (uint32_t base = 0; base < total; base += 1024u) {
+        const uint32_t p = base + threadIdx.x;
+        const uint32_t f = (p < total && T.list_dest[p] == d) ? 1u : 0u;
+        uint32_t sum;
+        const uint32_t ex = block_exclusive_scan(f, warp_sums, &sum);
+        if (f) T.list_pos[p] = carry + ex;
+        carry += sum;
+    }
+}
+
+// the agent leaves: record written, cell vacated, slot emptied and pushed, Counts decremented (decrement_counts,
+// allocation_map.rs:291-301), occupancies of its house / office decremented (remove_migrators, :165-192)
+__global__ void __launch_bounds__(256) k_travel_pack(Params P, DevPtrs D, TravelArgs A, TravelPtrs T, TravelRecord* __restrict__ send, uint32_t stride,
+                                                      uint32_t free_top) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    TravelVars* tv = T.tv;
+    const uint32_t total = min(tv->total, T.list_cap);
+    if (p >= total) return;
+    uint32_t dest, j;
+    if (A.kind == TRAVEL_MIGRATE) {
+        if (p >= tv->n_send) return;  // surplus candidates stay
+        dest = 0;
+        while (!(p >= tv->base[dest] && p < tv->base[dest] + tv->cnt[dest])) ++dest;
+        j = p - tv->base[dest];
+    } else {
+        dest = T.list_dest[p];
+        if (dest >= (uint32_t)T.n_regions) return;
+        j = T.list_pos[p];
+    }
+    const uint32_t i = T.list_slot[p];
     const uint32_t s = D.st[i];
     TravelRecord r;
     r.st = s; r.t0 = D.t0[i]; r.home = D.home[i]; r.work = D.work[i]; r.reg = D.reg[i]; r.slot = i; r.from = (uint32_t)P.region; r.pad = 0;
-    out[j] = r;
-    const uint32_t c = D.cell[i];
-    D.grid[P.cell_offset(c)] = 0;
+    if (j + 1u < stride) send[(size_t)dest * stride + 1u + j] = r;
+    D.grid[P.cell_offset(D.cell[i])] = 0;
     D.st[i] = ST_ABSENT;
     D.prop[i] = 0;
     atomicSub(D.tot + count_category(s), 1u);
+    // free_slots.push_back: migrators in send order (remove_migrators walks the per-region lists), commuters in selection order
+    T.free_stack[free_top + p] = i;
+    if (A.kind == TRAVEL_MIGRATE) {
+        const uint32_t old = atomicSub(&T.occ_house[house_rank(P, r.home)], 1u);
+        if (old == OCC_ABSENT || old == 0u) atomicOr(&tv->err, TERR_NO_HOUSE);  // "Could not find house"
+        if (((s >> ST_WS_SHIFT) & 3u) != WS_NA) {
+            const uint32_t oldo = atomicSub(&T.occ_office[office_rank(P, r.work)], 1u);
+            if (oldo == OCC_ABSENT || oldo == 0u) atomicOr(&tv->err, TERR_NO_OFFICE);
+        }
+    }
 }
 
-// arrival k -> slot in_slot[k].  Citizen::from_migrator / from_commuter (citizen/mod.rs:113-154): immunity, vaccinated,
-// uses_public_transport and the disease state travel; hospitalized, isolated, work_quarantined reset; work status becomes
-// NA (migrator) or Normal (commuter); current_area = the housing strip.  The cell is assigned by the placement rounds.
-__global__ void __launch_bounds__(256) k_travel_install(Params P, DevPtrs D, TravelArgs A, const TravelRecord* __restrict__ in, uint32_t n_in,
-                                                         const uint32_t* __restrict__ in_slot, const uint32_t* __restrict__ in_home,
-                                                         const uint32_t* __restrict__ in_work) {
+// ---- arriving -----------------------------------------------------------------------------------------------------------
+// recv: one segment per source region (header + records) -> arrivals[k], k ascending in (source region, index)
+__global__ void __launch_bounds__(256) k_travel_gather(TravelPtrs T, const TravelRecord* __restrict__ recv, uint32_t stride, int kind) {
+    const uint32_t s = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t cnt = min(recv[(size_t)s * stride].st, stride - 1u);
+    if (j >= cnt) return;
+    uint32_t k = j;
+    for (uint32_t q = 0; q < s; ++q) k += min(recv[(size_t)q * stride].st, stride - 1u);
+    if (k >= T.list_cap) { atomicOr(&T.tv->err, TERR_LIST_OVERFLOW); return; }
+    T.arrivals[k] = recv[(size_t)s * stride + 1u + j];
+}
+
+// migrators: arr_widx[k] = number of working arrivals before k; tv->n_working = their total (they pop an office each)
+__global__ void __launch_bounds__(1024) k_travel_wscan(TravelPtrs T, uint32_t n_in) {
+    __shared__ uint32_t warp_sums[32];
+    uint32_t carry = 0;
+    for (uint32_t base = 0; base < n_in; base += 1024u) {
+        const uint32_t k = base + threadIdx.x;
+        const uint32_t f = (k < n_in && ((T.arrivals[k].st >> ST_WS_SHIFT) & 3u) != WS_NA) ? 1u : 0u;
+        uint32_t sum;
+        const uint32_t ex = block_exclusive_scan(f, warp_sums, &sum);
+        if (k < n_in) T.arr_widx[k] = f ? carry + ex : 0xFFFFFFFFu;
+        carry += sum;
+    }
+    if (threadIdx.x == 0) T.tv->n_working = carry;
+}
+
+// ---- water filling -------------------------------------------------------------------------------------------------------
+// per-block histogram of the occupancy levels 0 .. CAP-1 (areas at CAP or more, or absent, cannot be popped usefully)
+template <uint32_t CAP>
+__global__ void __launch_bounds__(256) k_occ_block_hist(const uint32_t* __restrict__ occ, uint32_t n, uint32_t* __restrict__ bh) {
+    __shared__ uint32_t h[CAP];
+    for (uint32_t l = threadIdx.x; l < CAP; l += blockDim.x) h[l] = 0;
+    __syncthreads();
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n) {
+        const uint32_t o = occ[r];
+        if (o < CAP) atomicAdd(&h[o], 1u);
+    }
+    __syncthreads();
+    for (uint32_t l = threadIdx.x; l < CAP; l += blockDim.x) bh[(size_t)blockIdx.x * CAP + l] = h[l];
+}
+// the level structure of K pops.  k_src: K is read from *k_src when non-null (a device-side count), else k_arg.
+template <uint32_t CAP>
+__global__ void __launch_bounds__(1024) k_occ_plan(const uint32_t* __restrict__ bh, uint32_t n_blocks, FillPlan* __restrict__ plan, const uint32_t* k_src, uint32_t k_arg,
+                                                    TravelVars* tv, uint32_t err_bit) {
+    __shared__ uint32_t H[CAP];
+    for (uint32_t l = threadIdx.x; l < CAP; l += blockDim.x) H[l] = 0;
+    __syncthreads();
+    for (uint32_t idx = threadIdx.x; idx < n_blocks * CAP; idx += blockDim.x) {
+        const uint32_t v = bh[idx];
+        if (v) atomicAdd(&H[idx % CAP], v);
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    const uint32_t K = k_src ? *k_src : k_arg;
+    plan->K = K; plan->L = 0; plan->l_last = 0; plan->last_count = 0;
+    if (K == 0) return;
+    uint32_t L = 0;
+    while (L < CAP && H[L] == 0) ++L;
+    uint64_t cum = 0, n_le = 0;
+    bool done = false;
+    for (uint32_t l = L; l < CAP; ++l) {
+        n_le += H[l];
+        plan->start[l] = (uint32_t)cum;
+        if (cum + n_le >= K) { plan->l_last = l; plan->last_count = K - (uint32_t)cum; done = true; break; }
+        cum += n_le;
+    }
+    plan->L = L;
+    if (!done) {  // "Couldn't find any house / offices with free space!" (allocation_map.rs:222, :254)
+        plan->K = 0;
+        atomicOr(&tv->err, err_bit);
+    }
+}
+// pref[l * n_blocks + b] = number of areas with occupancy <= l in blocks before b, for the levels the plan uses
+template <uint32_t CAP>
+__global__ void __launch_bounds__(1024) k_occ_prefix(const uint32_t* __restrict__ bh, uint32_t n_blocks, const FillPlan* __restrict__ plan, uint32_t* __restrict__ pref) {
+    __shared__ uint32_t warp_sums[32];
+    const uint32_t l = blockIdx.x;
+    if (plan->K == 0 || l < plan->L || l > plan->l_last) return;
+    uint32_t carry = 0;
+    for (uint32_t base = 0; base < n_blocks; base += 1024u) {
+        const uint32_t b = base + threadIdx.x;
+        uint32_t v = 0;
+        if (b < n_blocks)
+            for (uint32_t j = plan->L; j <= l; ++j) v += bh[(size_t)b * CAP + j];
+        uint32_t sum;
+        const uint32_t ex = block_exclusive_scan(v, warp_sums, &sum);
+        if (b < n_blocks) pref[(size_t)l * n_blocks + b] = carry + ex;
+        carry += sum;
+    }
+}
+// pop p -> the area it returns (index in tie order)
+template <uint32_t CAP>
+__global__ void __launch_bounds__(256) k_occ_assign(const uint32_t* __restrict__ occ, uint32_t n, uint32_t n_blocks, const FillPlan* __restrict__ plan,
+                                                     const uint32_t* __restrict__ pref, uint32_t* __restrict__ out, const uint32_t* __restrict__ pop_index, uint32_t n_arrivals) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_arrivals) return;
+    const uint32_t p = pop_index ? pop_index[k] : k;  // which pop of this heap serves arrival k (0xFFFFFFFF: none)
+    if (p >= plan->K) { out[k] = 0xFFFFFFFFu; return; }
+    uint32_t l = plan->L;
+    while (l < plan->l_last && p >= plan->start[l + 1]) ++l;
+    const uint32_t q = p - plan->start[l];
+    const uint32_t* pl = pref + (size_t)l * n_blocks;
+    uint32_t lo = 0, hi = n_blocks;  // largest b with pl[b] <= q
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (pl[mid] <= q) lo = mid; else hi = mid;
+    }
+    uint32_t left = q - pl[lo];
+    uint32_t r = lo * 256u;
+    const uint32_t end = min(r + 256u, n);
+    for (; r < end; ++r)
+        if (occ[r] <= l) {
+            if (left == 0) break;
+            --left;
+        }
+    out[k] = r;
+}
+// every area that was popped comes back with one more occupant per pop
+template <uint32_t CAP>
+__global__ void __launch_bounds__(256) k_occ_update(uint32_t* __restrict__ occ, uint32_t n, uint32_t n_blocks, const FillPlan* __restrict__ plan, const uint32_t* __restrict__ pref) {
+    __shared__ uint32_t warp_sums[32];
+    if (plan->K == 0) return;
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t o = r < n ? occ[r] : OCC_ABSENT;
+    const uint32_t L = plan->L, l_last = plan->l_last;
+    const uint32_t f = o <= l_last ? 1u : 0u;
+    uint32_t sum;
+    const uint32_t ex = block_exclusive_scan(f, warp_sums, &sum);
+    if (!f) return;
+    const uint32_t rank_last = pref[(size_t)l_last * n_blocks + blockIdx.x] + ex;
+    occ[r] = o + (l_last - max(o, L)) + (rank_last < plan->last_count ? 1u : 0u);
+}
+
+// arrival k -> the k-th slot from the top of the free stack.  Citizen::from_migrator / from_commuter (citizen/mod.rs:113-154):
+// immunity, vaccinated, uses_public_transport and the disease state travel; hospitalized, isolated, work_quarantined reset;
+// work status becomes NA (migrator) or Normal (commuter); current_area = the housing strip.  The cell is assigned by the
+// placement rounds.
+__global__ void __launch_bounds__(256) k_travel_install(Params P, DevPtrs D, TravelArgs A, TravelPtrs T, uint32_t n_in, uint32_t free_top) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n_in) return;
-    const TravelRecord r = in[k];
-    const uint32_t i = in_slot[k];
+    const TravelRecord r = T.arrivals[k];
+    const uint32_t i = T.free_stack[free_top - 1u - k];
     const uint32_t keep = ST_STATE_MASK | (3u << ST_SEV_SHIFT) | (7u << ST_IMM_SHIFT) | ST_VACC | ST_PT | (ST_DAY_MAX << ST_DAY_SHIFT);
     const uint32_t ws = A.kind == TRAVEL_MIGRATE ? WS_NA : WS_NORMAL;
     const uint32_t s = (r.st & keep) | (ws << ST_WS_SHIFT) | (AK_HOUSING << ST_AREA_SHIFT);
@@ -136,93 +398,141 @@ __global__ void __launch_bounds__(256) k_travel_install(Params P, DevPtrs D, Tra
     D.wsa[i] = 0;
     D.prop[i] = 0;
     if (A.kind == TRAVEL_MIGRATE) {
-        D.home[i] = in_home[k];
-        D.work[i] = in_work[k];
+        const uint32_t house = T.arr_house[k];
+        D.home[i] = house != 0xFFFFFFFFu ? house_origin_of_rank(P, house) : 0u;
+        D.work[i] = 0;  // WorkStatus::NA after from_migrator: the office only counts in the occupancy heap
         D.reg[i] = self | (self << 8);
     } else {
         D.home[i] = r.home;
         const bool assign_office = A.hour == 7u;  // sic: the absolute hour (allocation_map.rs:260), i.e. the first day only
-        D.work[i] = assign_office ? in_work[k] : r.work;
+        const uint32_t office = assign_office ? T.arr_office[k] : 0xFFFFFFFFu;
+        D.work[i] = office != 0xFFFFFFFFu ? office_origin_of_rank(P, office) : r.work;
         D.reg[i] = (r.reg & 0xFFu) | ((assign_office ? self : ((r.reg >> 8) & 0xFFu)) << 8);
     }
     atomicAdd(D.tot + count_category(s), 1u);
 }
 
 // ---- placement rounds (select_starting_points, allocation_map.rs:339-347) ------------------------------------------
-// Arrival k proposes in round a the cell drawn from Philox(seed, k, hour, DOM_ARRIVAL) block a, x in [sx, ex), y in [sy, ey).
-__device__ __forceinline__ uint32_t arrival_cell(const Params& P, const TravelArgs& A, uint32_t k, uint32_t attempt) {
-    const U4 o = philox4x32_10(k, A.hour, attempt, DOM_ARRIVAL, (uint32_t)P.seed, (uint32_t)(P.seed >> 32));
+// In round a every still-unplaced arrival k walks its own candidate sequence Philox(seed, k, hour, DOM_ARRIVAL) blocks
+// a * PLACE_TRIES .. a * PLACE_TRIES + PLACE_TRIES - 1 (x in [sx, ex), y in [sy, ey)) and proposes the FIRST candidate that is
+// vacant now (start-of-hour occupants and earlier rounds' winners count as occupied); of several proposals for one cell the
+// lowest k wins; a loser, or an arrival whose candidates were all occupied, tries again in the next round.
+constexpr uint32_t PLACE_TRIES = 8;
+__device__ __forceinline__ uint32_t arrival_cell(const Params& P, const TravelArgs& A, uint32_t k, uint32_t block) {
+    const U4 o = philox4x32_10(k, A.hour, block, DOM_ARRIVAL, (uint32_t)P.seed, (uint32_t)(P.seed >> 32));
     const Rect& r = A.kind == TRAVEL_MIGRATE ? P.housing() : P.transport();
     const uint32_t x = (uint32_t)r.sx + __umulhi(o.x, (uint32_t)(r.ex - r.sx));
     const uint32_t y = (uint32_t)r.sy + __umulhi(o.y, (uint32_t)(r.ey - r.sy));
     return (y << CELL_BITS) | x;
 }
+__device__ __forceinline__ uint32_t first_vacant_candidate(const Params& P, const DevPtrs& D, const TravelArgs& A, uint32_t k, uint32_t attempt) {
+    for (uint32_t t = 0; t < PLACE_TRIES; ++t) {
+        const uint32_t c = arrival_cell(P, A, k, attempt * PLACE_TRIES + t);
+        if (D.grid[P.cell_offset(c)] == 0) return c;
+    }
+    return 0xFFFFFFFFu;
+}
 __device__ __forceinline__ uint32_t hash_cell(uint32_t c) { return (c * 0x9E3779B1u) >> 7; }
 
-__global__ void __launch_bounds__(256) k_travel_propose(Params P, DevPtrs D, TravelArgs A, uint32_t n_in, uint32_t attempt, const uint8_t* __restrict__ placed,
-                                                         uint32_t* __restrict__ table_keys, uint32_t* __restrict__ table_vals, uint32_t table_mask) {
+__global__ void __launch_bounds__(256) k_travel_round_begin(TravelPtrs T) {
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx <= T.table_mask) { T.table_keys[idx] = 0u; T.table_vals[idx] = 0xFFFFFFFFu; }
+    if (idx == 0) T.tv->pending = 0;
+}
+__global__ void __launch_bounds__(256) k_travel_propose(Params P, DevPtrs D, TravelArgs A, TravelPtrs T, uint32_t n_in, uint32_t attempt) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n_in || placed[k]) return;
-    const uint32_t c = arrival_cell(P, A, k, attempt);
-    if (D.grid[P.cell_offset(c)] != 0) return;  // occupied (also by earlier rounds' winners)
-    uint32_t slot = hash_cell(c) & table_mask;
+    if (k >= n_in || T.placed[k]) return;
+    const uint32_t c = first_vacant_candidate(P, D, A, k, attempt);
+    T.list_pos[k] = c;  // this round's proposal (list_pos is free during unpack)
+    if (c == 0xFFFFFFFFu) return;
+    uint32_t slot = hash_cell(c) & T.table_mask;
     for (;;) {
-        const uint32_t old = atomicCAS(&table_keys[slot], 0u, c + 1u);
-        if (old == 0u || old == c + 1u) { atomicMin(&table_vals[slot], k); return; }
-        slot = (slot + 1u) & table_mask;
+        const uint32_t old = atomicCAS(&T.table_keys[slot], 0u, c + 1u);
+        if (old == 0u || old == c + 1u) { atomicMin(&T.table_vals[slot], k); return; }
+        slot = (slot + 1u) & T.table_mask;
     }
 }
-__global__ void __launch_bounds__(256) k_travel_grant(Params P, DevPtrs D, TravelArgs A, uint32_t n_in, uint32_t attempt, uint8_t* __restrict__ placed,
-                                                       const uint32_t* __restrict__ in_slot, const uint32_t* __restrict__ table_keys,
-                                                       const uint32_t* __restrict__ table_vals, uint32_t table_mask, uint32_t* __restrict__ pending) {
+__global__ void __launch_bounds__(256) k_travel_grant(Params P, DevPtrs D, TravelArgs A, TravelPtrs T, uint32_t n_in, uint32_t free_top) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n_in || placed[k]) return;
-    const uint32_t c = arrival_cell(P, A, k, attempt);
-    uint32_t slot = hash_cell(c) & table_mask;
+    if (k >= n_in || T.placed[k]) return;
+    const uint32_t c = T.list_pos[k];
     bool won = false;
-    for (;;) {
-        const uint32_t key = table_keys[slot];
-        if (key == 0u) break;
-        if (key == c + 1u) { won = table_vals[slot] == k; break; }
-        slot = (slot + 1u) & table_mask;
+    if (c != 0xFFFFFFFFu) {
+        uint32_t slot = hash_cell(c) & T.table_mask;
+        for (;;) {
+            const uint32_t key = T.table_keys[slot];
+            if (key == 0u) break;
+            if (key == c + 1u) { won = T.table_vals[slot] == k; break; }
+            slot = (slot + 1u) & T.table_mask;
+        }
     }
     if (won) {
-        const uint32_t i = in_slot[k];
+        const uint32_t i = T.free_stack[free_top - 1u - k];
         D.cell[i] = c;
         D.grid[P.cell_offset(c)] = (uint8_t)cell_byte(P, D.st[i]);
-        placed[k] = 1;
+        T.placed[k] = 1;
     } else {
-        atomicAdd(pending, 1u);
+        atomicAdd(&T.tv->pending, 1u);
     }
 }
 
 // ---- launchers ---------------------------------------------------------------------------------------------------------
 static inline unsigned blocks_for(uint32_t n) { return (n + 255u) / 256u; }
 
-void launch_travel_select(const Params& P, const DevPtrs& D, const TravelArgs& A, uint32_t* block_counts, uint32_t* total, uint32_t* out_slots,
-                          uint32_t* out_dest, int phase, cudaStream_t s) {
+unsigned launch_travel_leave(const Params& P, const DevPtrs& D, const TravelArgs& A, const TravelPtrs& T, uint32_t* block_counts, TravelRecord* send,
+                             uint32_t stride, uint32_t free_top, cudaStream_t s) {
     const unsigned nb = blocks_for(P.n);
-    if (phase == 0) {
-        k_travel_flag_count<<<nb, 256, 0, s>>>(P, D, A, block_counts);
-        k_travel_scan<<<1, 1024, 0, s>>>(block_counts, nb, total);
-    } else {
-        k_travel_scatter<<<nb, 256, 0, s>>>(P, D, A, block_counts, out_slots, out_dest);
+    k_travel_flag_count<<<nb, 256, 0, s>>>(P, D, A, block_counts);
+    k_travel_scan<<<1, 1024, 0, s>>>(block_counts, nb, T.tv);
+    k_travel_scatter<<<nb, 256, 0, s>>>(P, D, A, T, block_counts);
+    k_travel_plan<<<1, 1024, 0, s>>>(P, A, T, send, stride);
+    unsigned launches = 5;
+    if (A.kind == TRAVEL_COMMUTE) { k_travel_rank<<<(unsigned)T.n_regions, 1024, 0, s>>>(T); ++launches; }
+    k_travel_pack<<<blocks_for(T.list_cap), 256, 0, s>>>(P, D, A, T, send, stride, free_top);
+    return launches;
+}
+
+template <uint32_t CAP>
+static unsigned water_fill(uint32_t* occ, uint32_t n, uint32_t* bh, uint32_t* pref, FillPlan* plan, const uint32_t* k_src, uint32_t k_arg, TravelVars* tv,
+                           uint32_t err_bit, uint32_t* out, const uint32_t* pop_index, uint32_t n_arrivals, cudaStream_t s) {
+    const unsigned nb = blocks_for(n);
+    k_occ_block_hist<CAP><<<nb, 256, 0, s>>>(occ, n, bh);
+    k_occ_plan<CAP><<<1, 1024, 0, s>>>(bh, nb, plan, k_src, k_arg, tv, err_bit);
+    k_occ_prefix<CAP><<<CAP, 1024, 0, s>>>(bh, nb, plan, pref);
+    k_occ_assign<CAP><<<blocks_for(n_arrivals), 256, 0, s>>>(occ, n, nb, plan, pref, out, pop_index, n_arrivals);
+    k_occ_update<CAP><<<nb, 256, 0, s>>>(occ, n, nb, plan, pref);
+    return 5;
+}
+
+unsigned launch_travel_arrive(const Params& P, const DevPtrs& D, const TravelArgs& A, const TravelPtrs& T, const TravelRecord* recv, uint32_t stride,
+                              uint32_t n_in, uint32_t max_segment, uint32_t n_houses, uint32_t n_offices, uint32_t free_top, cudaStream_t s) {
+    unsigned launches = 0;
+    k_travel_gather<<<dim3(blocks_for(max_segment), (unsigned)T.n_regions), 256, 0, s>>>(T, recv, stride, A.kind);
+    ++launches;
+    if (A.kind == TRAVEL_MIGRATE) {
+        // assimilate_migrators (allocation_map.rs:214-243): every arrival pops a house, the working ones an office as well
+        k_travel_wscan<<<1, 1024, 0, s>>>(T, n_in);
+        ++launches;
+        launches += water_fill<HOUSE_CAP>(T.occ_house, n_houses, T.bh_house, T.pref_house, T.plan_house, nullptr, n_in, T.tv, TERR_HOUSES_FULL, T.arr_house, nullptr, n_in, s);
+        launches += water_fill<OFFICE_CAP>(T.occ_office, n_offices, T.bh_office, T.pref_office, T.plan_office, &T.tv->n_working, 0, T.tv, TERR_OFFICES_FULL, T.arr_office,
+                                           T.arr_widx, n_in, s);
+    } else if (A.hour == 7u) {
+        // assimilate_commuters (allocation_map.rs:245-277): an office is assigned at the absolute hour 7 only (:260)
+        launches += water_fill<OFFICE_CAP>(T.occ_office, n_offices, T.bh_office, T.pref_office, T.plan_office, nullptr, n_in, T.tv, TERR_OFFICES_FULL, T.arr_office, nullptr,
+                                           n_in, s);
     }
+    k_travel_install<<<blocks_for(n_in), 256, 0, s>>>(P, D, A, T, n_in, free_top);
+    return launches + 1;
 }
-void launch_travel_pack(const Params& P, const DevPtrs& D, const uint32_t* send_slots, uint32_t n_send, TravelRecord* out, cudaStream_t s) {
-    if (n_send) k_travel_pack<<<blocks_for(n_send), 256, 0, s>>>(P, D, send_slots, n_send, out);
-}
-void launch_travel_install(const Params& P, const DevPtrs& D, const TravelArgs& A, const TravelRecord* in, uint32_t n_in, const uint32_t* in_slot,
-                           const uint32_t* in_home, const uint32_t* in_work, cudaStream_t s) {
-    if (n_in) k_travel_install<<<blocks_for(n_in), 256, 0, s>>>(P, D, A, in, n_in, in_slot, in_home, in_work);
-}
-void launch_travel_round(const Params& P, const DevPtrs& D, const TravelArgs& A, uint32_t n_in, uint32_t attempt, uint8_t* placed, const uint32_t* in_slot,
-                         uint32_t* table_keys, uint32_t* table_vals, uint32_t table_mask, uint32_t* pending, cudaStream_t s) {
-    cudaMemsetAsync(table_keys, 0, ((size_t)table_mask + 1) * sizeof(uint32_t), s);
-    cudaMemsetAsync(table_vals, 0xFF, ((size_t)table_mask + 1) * sizeof(uint32_t), s);
-    cudaMemsetAsync(pending, 0, sizeof(uint32_t), s);
-    k_travel_propose<<<blocks_for(n_in), 256, 0, s>>>(P, D, A, n_in, attempt, placed, table_keys, table_vals, table_mask);
-    k_travel_grant<<<blocks_for(n_in), 256, 0, s>>>(P, D, A, n_in, attempt, placed, in_slot, table_keys, table_vals, table_mask, pending);
+
+unsigned launch_travel_rounds(const Params& P, const DevPtrs& D, const TravelArgs& A, const TravelPtrs& T, uint32_t n_in, uint32_t first_attempt, uint32_t n_rounds,
+                              uint32_t free_top, cudaStream_t s) {
+    for (uint32_t a = 0; a < n_rounds; ++a) {
+        k_travel_round_begin<<<blocks_for(T.table_mask + 1u), 256, 0, s>>>(T);
+        k_travel_propose<<<blocks_for(n_in), 256, 0, s>>>(P, D, A, T, n_in, first_attempt + a);
+        k_travel_grant<<<blocks_for(n_in), 256, 0, s>>>(P, D, A, T, n_in, free_top);
+    }
+    return 3 * n_rounds;
 }
 
 }  // namespace epi

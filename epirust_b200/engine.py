@@ -133,15 +133,18 @@ class Engine:
         return self.L.epi_capacity(self.h)
 
     # ---- traveller exchange (multi-region engines) ----
-    def travel_pack(self, hour, kind, send_ptr, capacity_records):
-        """send_ptr: device pointer (int).  Returns the per-destination record counts (host, numpy uint32[n_regions])."""
+    def travel_pack(self, hour, kind, send_ptr, stride_records):
+        """send_ptr: device pointer (int) of n_regions segments of stride_records records (segment d = header + the records for
+        region d).  Returns the per-destination record counts (host, numpy uint32[n_regions])."""
         counts = np.zeros(self.n_regions, np.uint32)
-        self._check(self.L.epi_travel_pack(self.h, hour, kind, C.c_void_p(send_ptr), capacity_records, _ptr(counts)))
+        self._check(self.L.epi_travel_pack(self.h, hour, kind, C.c_void_p(send_ptr), stride_records, _ptr(counts)))
         return counts
 
-    def travel_unpack(self, hour, kind, recv_ptr, counts_in):
-        counts_in = np.ascontiguousarray(counts_in, np.uint32)
-        self._check(self.L.epi_travel_unpack(self.h, hour, kind, C.c_void_p(recv_ptr), _ptr(counts_in)))
+    def travel_unpack(self, hour, kind, recv_ptr, stride_records):
+        """recv_ptr: device pointer of n_regions segments (segment s = header + the records region s sent).  Returns counts per source."""
+        counts_in = np.zeros(self.n_regions, np.uint32)
+        self._check(self.L.epi_travel_unpack(self.h, hour, kind, C.c_void_p(recv_ptr), stride_records, _ptr(counts_in)))
+        return counts_in
 
     def finish_hour(self, hour):
         c = EpiCounts()

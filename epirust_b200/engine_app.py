@@ -97,6 +97,15 @@ def arrival_capacity(plan, r, hours):
     return extra + extra // 8 + 1024
 
 
+def segment_capacity(plan):
+    """Records one (source, destination) segment must hold: twice the largest planned pair (migrator counts are binomial) + slack."""
+    most = 0
+    for k in ("migration", "commute"):
+        if plan[k] is not None:
+            most = max(most, int(plan[k].max()))
+    return 2 * most + 4096
+
+
 def output_file_format(output_dir, engine_id):
     """utils/util.rs:31-43"""
     d = os.path.join(output_dir, "output")
@@ -162,20 +171,18 @@ def run_region(args):
     travels = []
 
     def on_outgoing(hour, kind, send_buf, counts):  # TravelCounter::outgoing_migrators_added (travel_counter.rs:84-87)
-        if kind != _ffi.TRAVEL_MIGRATE:
+        if kind != _ffi.TRAVEL_MIGRATE or int(counts.sum()) == 0:
             return
-        at = 0
         for dest, c in enumerate(counts):
             c = int(c)
             if dest == region:
                 continue
-            state = (send_buf[at:at + c, 0] & 7).cpu().numpy() if c else np.zeros(0, np.int64)
-            at += c
+            state = (send_buf[dest, 1:1 + c, 0] & 7).cpu().numpy() if c else np.zeros(0, np.int64)
             travels.append((hour, plan["regions"][dest], int((state == 0).sum()), int((state == 1).sum()), int((state == 2).sum()), int((state == 3).sum())))
 
     start = time.time()
     with torch.cuda.stream(stream):
-        runner = MultiRegion([eng], plan, exchange=DistExchange(torch.device("cuda", local)), max_records=max(1 << 14, 4 * arrival_capacity(plan, region, 48)),
+        runner = MultiRegion([eng], plan, exchange=DistExchange(torch.device("cuda", local)), stride_records=segment_capacity(plan),
                              on_outgoing=on_outgoing)
         rows = np.zeros((1, max(hours - 1, 0), 7), np.uint32)
         done = 0

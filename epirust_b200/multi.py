@@ -4,9 +4,8 @@ Mirror of Epidemiology::run_multi_engine (engine/src/epidemiology_simulation.rs:
 (engine/src/transport/*.rs) replaced by an all-to-allv of packed traveller records between the GPUs:
 
   * DistExchange  -- one process per GPU, torch.distributed (NCCL over NVLink / NVSwitch; gloo for CPU tests of the
-                     plumbing): counts via all_to_all_single, then the records via all_to_all_single with split sizes.
-  * LocalExchange -- every region engine lives in this process (tests; several regions on one GPU): device-to-device
-                     copies.
+                     plumbing): ONE all_to_all_single with equal splits over padded segments whose headers carry the counts.
+  * exchange=None -- every region engine lives in this process (tests; several regions on one GPU): a device transpose.
 
 The orchestrator's barrier (orchestrator/src/ticks.rs:35-89) is implicit in the collective; its global termination rule
 (sum of exposed + infected + hospitalized over the regions == 0, ticks.rs:175-180) is `active_cases_everywhere`.
@@ -30,17 +29,10 @@ def exchange_hours(plan):
     return kinds
 
 
-def split_records(buf, counts):
-    """Views of a flat record buffer per peer."""
-    out, at = [], 0
-    for c in counts:
-        out.append(buf[at:at + int(c)])
-        at += int(c)
-    return out
-
-
 class DistExchange:
-    """all-to-allv over torch.distributed; `device` is the torch device of the record buffers."""
+    """all-to-all over torch.distributed; `device` is the torch device of the record buffers.  The buffers are padded (one
+    fixed-size segment per peer, the record count in the segment header), so ONE collective with equal splits moves counts
+    and payload together and no count exchange / host round trip precedes it."""
 
     def __init__(self, device, group=None):
         import torch.distributed as dist
@@ -48,19 +40,14 @@ class DistExchange:
         self.dist, self.group, self.device = dist, group, device
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
+        self._recv = None
 
-    def exchange(self, send_buf, send_counts):
-        """send_buf: [n, REC_WORDS] int32 tensor grouped by destination rank; send_counts: numpy[world].  Returns (recv_buf, recv_counts)."""
-        d = self.dist
-        sc = torch.as_tensor(np.asarray(send_counts, np.int64), device=self.device)
-        rc = torch.empty_like(sc)
-        d.all_to_all_single(rc, sc, group=self.group)
-        recv_counts = rc.cpu().numpy()
-        n_in = int(recv_counts.sum())
-        recv = torch.empty((n_in, REC_WORDS), dtype=torch.int32, device=self.device)
-        d.all_to_all_single(recv, send_buf[: int(np.sum(send_counts))], output_split_sizes=[int(c) for c in recv_counts],
-                            input_split_sizes=[int(c) for c in send_counts], group=self.group)
-        return recv, recv_counts.astype(np.uint32)
+    def exchange(self, send_buf):
+        """send_buf: [world, stride, REC_WORDS] int32, segment d addressed to rank d.  Returns recv of the same shape: segment s = what rank s sent."""
+        if self._recv is None or self._recv.shape != send_buf.shape:
+            self._recv = torch.empty_like(send_buf)
+        self.dist.all_to_all_single(self._recv.view(-1), send_buf.view(-1), group=self.group)
+        return self._recv
 
     def all_reduce_sum(self, values):
         t = torch.as_tensor(np.asarray(values, np.int64), device=self.device)
@@ -71,18 +58,21 @@ class DistExchange:
 class MultiRegion:
     """R region engines hosted by this process (R == 1 per process under torchrun)."""
 
-    def __init__(self, engines, plan, exchange=None, max_records=1 << 17, on_outgoing=None):
-        """on_outgoing(hour, kind, send_buf, counts): called per local engine after its leavers were packed (send_buf: [n, 8] int32
-        device tensor grouped by destination; counts: numpy[n_regions]) -- the hook of Listener::outgoing_migrators_added."""
+    def __init__(self, engines, plan, exchange=None, stride_records=1 << 15, on_outgoing=None):
+        """stride_records: capacity of one (source, destination) segment, header included.
+        on_outgoing(hour, kind, send_buf, counts): called per local engine after its leavers were packed (send_buf: [n_regions, stride, 8]
+        int32 device tensor, segment d = header + records for region d; counts: numpy[n_regions]) -- the hook of
+        Listener::outgoing_migrators_added."""
         self.engines = engines
         self.on_outgoing = on_outgoing
         self.plan = plan
         self.kinds = exchange_hours(plan)
         self.exchange = exchange  # None: all regions are local
         self.R = int(plan["n_regions"])
+        self.stride = int(stride_records)
         dev = torch.device("cuda", torch.cuda.current_device())
-        self.send = [torch.zeros((max_records, REC_WORDS), dtype=torch.int32, device=dev) for _ in engines]
-        self.max_records = max_records
+        # [local engine, destination region, record, word]
+        self.send = torch.zeros((len(engines), self.R, self.stride, REC_WORDS), dtype=torch.int32, device=dev)
 
     def next_exchange_hour(self, hour, last_hour):
         for h in range(hour, last_hour + 1):
@@ -91,28 +81,23 @@ class MultiRegion:
         return None
 
     def _do_exchange(self, hour, kind):
-        outs = []
-        for e, buf in zip(self.engines, self.send):
-            outs.append(e.travel_pack(hour, kind, buf.data_ptr(), self.max_records))
+        for i, e in enumerate(self.engines):
+            counts = e.travel_pack(hour, kind, self.send[i].data_ptr(), self.stride)
             if self.on_outgoing is not None:
-                e.sync()
-                self.on_outgoing(hour, kind, buf, outs[-1])
+                self.on_outgoing(hour, kind, self.send[i], counts)
         if self.exchange is None:
-            # local all-to-allv: region r receives, in source order, what every source addressed to it
-            parts = [split_records(buf, c) for buf, c in zip(self.send, outs)]
-            for r, e in enumerate(self.engines):
-                counts_in = np.array([outs[s][r] for s in range(self.R)], np.uint32)
-                if counts_in.sum() == 0:
-                    continue
-                recv = torch.cat([parts[s][r] for s in range(self.R)], dim=0).contiguous()
-                torch.cuda.current_stream().synchronize()
-                e.travel_unpack(hour, kind, recv.data_ptr(), counts_in)
-        else:
-            (e,), (buf,), (counts,) = self.engines, self.send, outs
-            recv, counts_in = self.exchange.exchange(buf, counts)
+            # every region is local: region r receives segment r of every source, in source order
+            for e in self.engines:
+                e.sync()
+            recv = self.send.transpose(0, 1).contiguous()
             torch.cuda.current_stream().synchronize()
-            if counts_in.sum():
-                e.travel_unpack(hour, kind, recv.data_ptr(), counts_in)
+            for r, e in enumerate(self.engines):
+                e.travel_unpack(hour, kind, recv[r].data_ptr(), self.stride)
+        else:
+            (e,) = self.engines
+            recv = self.exchange.exchange(self.send[0])
+            torch.cuda.current_stream().synchronize()
+            e.travel_unpack(hour, kind, recv.data_ptr(), self.stride)
 
     def run(self, first_hour, n_hours, rows_out=None):
         """Hours first_hour .. first_hour + n_hours - 1 of every local region.  Returns rows[n_local, n_hours, 7]."""

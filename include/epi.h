@@ -148,19 +148,25 @@ int epi_intervention_events(const epi_engine* e, epi_intervention_event* out, ui
 
 /* ---- multi-region: the traveller exchange (engine/src/epidemiology_simulation.rs:391-503) -------------------------------
  * Per exchange hour (h % 24 == 0 migrators inside the migration window, h % 24 in {7, 17} commuters) the caller runs
- *   epi_step(hour) -> epi_travel_pack -> all-to-allv of the records (NCCL over NVLink; torch.distributed in this repo)
+ *   epi_step(hour) -> epi_travel_pack -> all-to-all of the segments (NCCL over NVLink; torch.distributed in this repo)
  *   -> epi_travel_unpack -> epi_finish_hour.
  * Replaces Transport::send_* / receive_* (engine/src/transport/mod.rs:34-42, mpi_transport.rs:78-215) around
- * remove_* / assimilate_* (allocation_map.rs:165-277).  Records never leave device memory; the host sees counts and
- * the index lists needed for the reference's sequential bookkeeping (occupancy heaps, agent slots). */
+ * remove_* / assimilate_* (allocation_map.rs:165-277).  Records never leave device memory and all of the reference's
+ * sequential bookkeeping (allotment of migrators to regions, free agent slots, house / office occupancy heaps) runs on the
+ * device; the host only sees the per-region record counts.
+ *
+ * Buffer layout (send and receive alike, DEVICE memory): n_regions segments of stride_records records of
+ * EPI_TRAVEL_RECORD_BYTES each.  Record 0 of a segment is a header whose first 32-bit word is the number of records that
+ * follow (<= stride_records - 1).  In the send buffer segment d is addressed to region d; after an all-to-all with equal
+ * splits segment s of the receive buffer holds what region s sent here. */
 /* Selects the leaving agents (Citizen::is_commuter / can_migrate + gen_bool(percent_outgoing), citizen/mod.rs:456-495),
  * allots migrators to regions (EngineMigrationPlan::alloc_outgoing_to_regions, engine_migration_plan.rs:51-77), writes
- * their records grouped by destination region into send_buf (DEVICE memory, room for capacity_records records) and
- * removes them from the region.  counts_out[n_regions] (HOST) = records per destination. */
-int epi_travel_pack(epi_engine* e, uint32_t hour, int kind, void* send_buf, uint64_t capacity_records, uint32_t* counts_out);
-/* Installs the arrivals: recv_buf (DEVICE) holds sum(counts_in) records ordered by source region (counts_in[n_regions],
- * HOST).  assimilate_migrators / assimilate_commuters (allocation_map.rs:214-277). */
-int epi_travel_unpack(epi_engine* e, uint32_t hour, int kind, const void* recv_buf, const uint32_t* counts_in);
+ * their records into the destination's segment of send_buf and removes them from the region.  counts_out[n_regions]
+ * (HOST) = records per destination.  Every segment header is written, also when nobody travels. */
+int epi_travel_pack(epi_engine* e, uint32_t hour, int kind, void* send_buf, uint64_t stride_records, uint32_t* counts_out);
+/* Installs the arrivals of recv_buf in order of source region.  assimilate_migrators / assimilate_commuters
+ * (allocation_map.rs:214-277).  counts_in[n_regions] (HOST, may be NULL) receives the records per source region. */
+int epi_travel_unpack(epi_engine* e, uint32_t hour, int kind, const void* recv_buf, uint64_t stride_records, uint32_t* counts_in);
 /* The tail of the multi-engine hour (epidemiology_simulation.rs:492-503): Counts after the travel adjustments,
  * process_interventions, and stop_simulation's MultiEngine arm (:564-571, records lockdown.zero_infection_hour). */
 int epi_finish_hour(epi_engine* e, uint32_t hour, epi_counts* out);

@@ -203,9 +203,11 @@ struct RegionEngine : Engine {
 
     // select_starting_points (allocation_map.rs:339-347): `n` distinct vacant cells of area, x in [sx, ex), y in [sy, ey).
     // The reference reservoir-samples the vacant cells; convention here (and in the CUDA path): rounds.  In round a every
-    // still-unplaced arrival k proposes the cell drawn from Philox(seed, k, hour, DOM_ARRIVAL) block a; a proposal for an
-    // occupied cell fails; of several proposals for one free cell the lowest k wins; winners' cells are occupied from the
-    // next round on.
+    // still-unplaced arrival k walks its own candidate sequence Philox(seed, k, hour, DOM_ARRIVAL) blocks
+    // a * PLACE_TRIES .. a * PLACE_TRIES + PLACE_TRIES - 1 and proposes the FIRST candidate that is vacant now (start-of-hour
+    // occupants and earlier rounds' winners count as occupied); of several proposals for one cell the lowest k wins; a
+    // loser, or an arrival whose candidates were all occupied, tries again in the next round.
+    static constexpr uint32_t PLACE_TRIES = 8;
     std::vector<Point> select_starting_points(const Area& area, size_t n, Hour hour) {
         std::vector<Point> out(n);
         std::vector<uint8_t> placed(n, 0);
@@ -216,20 +218,26 @@ struct RegionEngine : Engine {
             if (attempt > 64) throw std::runtime_error("Not enough locations are available for travellers");
             PointMap round; round.init(left);
             std::vector<Point> prop(n);
+            std::vector<uint8_t> has_prop(n, 0);
             for (size_t k = 0; k < n; ++k) {
                 if (placed[k]) continue;
                 Rng r; r.mode = Rng::KEYED; r.seed = seed; r.agent = (uint32_t)k; r.hour = hour; r.domain = DOM_ARRIVAL;
-                uint32_t o[4];
-                r.block(attempt, o);
-                Point p{area.start_offset.x + (int)mulhi32(o[0], w), area.start_offset.y + (int)mulhi32(o[1], h)};
-                prop[k] = p;
-                if (!map.is_cell_vacant(p) || taken.contains_key(p)) continue;
+                for (uint32_t t = 0; t < PLACE_TRIES; ++t) {
+                    uint32_t o[4];
+                    r.block(attempt * PLACE_TRIES + t, o);
+                    Point p{area.start_offset.x + (int)mulhi32(o[0], w), area.start_offset.y + (int)mulhi32(o[1], h)};
+                    if (!map.is_cell_vacant(p) || taken.contains_key(p)) continue;
+                    prop[k] = p;
+                    has_prop[k] = 1;
+                    break;
+                }
+                if (!has_prop[k]) continue;
                 Citizen marker; marker.id = (uint32_t)k;
-                Citizen& first = round.entry_or_insert(p, marker);  // ascending k: the first entry is the lowest k
+                Citizen& first = round.entry_or_insert(prop[k], marker);  // ascending k: the first entry is the lowest k
                 (void)first;
             }
             for (size_t k = 0; k < n; ++k) {
-                if (placed[k]) continue;
+                if (placed[k] || !has_prop[k]) continue;
                 const Citizen* win = round.get(prop[k]);
                 if (win && win->id == (uint32_t)k) { out[k] = prop[k]; placed[k] = 1; --left; Citizen m; taken.insert(prop[k], m); }
             }

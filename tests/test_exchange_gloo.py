@@ -1,4 +1,4 @@
-"""The N > 1 plumbing on CPU: world_size-2 gloo run of the all-to-allv that carries the traveller records
+"""The N > 1 plumbing on CPU: world_size-2 gloo run of the padded all-to-all that carries the traveller records
 (epirust_b200.multi.DistExchange), with CPU tensors standing in for the device buffers."""
 import os
 import socket
@@ -19,30 +19,32 @@ def _free_port():
 def _worker(rank, world, port, ret):
     import torch.distributed as dist
 
-    from epirust_b200.multi import DistExchange, REC_WORDS, split_records
+    from epirust_b200.multi import DistExchange, REC_WORDS
 
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         x = DistExchange(torch.device("cpu"))
-        # rank r sends (r + 1) * (d + 2) records to rank d; record word 0 = sender, word 1 = destination, word 2 = index
-        counts = np.array([(rank + 1) * (d + 2) if d != rank else 0 for d in range(world)], np.uint32)
-        recs = []
+        stride = 16
+        # rank r sends (r + 1) * (d + 2) records to rank d; header word 0 = count; record word 0 = sender, 1 = destination, 2 = index
+        counts = np.array([(rank + 1) * (d + 2) if d != rank else 0 for d in range(world)], np.int64)
+        send = torch.zeros((world, stride, REC_WORDS), dtype=torch.int32)
         for d in range(world):
+            send[d, 0, 0] = int(counts[d])
             for k in range(int(counts[d])):
-                recs.append([rank, d, k] + [0] * (REC_WORDS - 3))
-        send = torch.tensor(recs, dtype=torch.int32).reshape(-1, REC_WORDS)
-        recv, counts_in = x.exchange(send, counts)
-        want_in = np.array([(s + 1) * (rank + 2) if s != rank else 0 for s in range(world)], np.uint32)
-        ok = (counts_in == want_in).all() and recv.shape[0] == int(want_in.sum())
-        for s, part in enumerate(split_records(recv, counts_in)):
+                send[d, 1 + k, :3] = torch.tensor([rank, d, k], dtype=torch.int32)
+        recv = x.exchange(send)
+        want_in = np.array([(s + 1) * (rank + 2) if s != rank else 0 for s in range(world)], np.int64)
+        ok = recv.shape == send.shape and recv[:, 0, 0].tolist() == want_in.tolist()
+        for s in range(world):
+            part = recv[s, 1:1 + int(want_in[s])]
             ok = ok and bool((part[:, 0] == s).all()) and bool((part[:, 1] == rank).all()) and part[:, 2].tolist() == list(range(int(want_in[s])))
         total = x.all_reduce_sum([int(counts.sum())])[0]
         ok = ok and total == sum((r + 1) * (d + 2) for r in range(world) for d in range(world) if d != r)
-        # an exchange in which nobody travels still works (empty tensors)
-        recv2, counts2 = x.exchange(torch.zeros((0, REC_WORDS), dtype=torch.int32), np.zeros(world, np.uint32))
-        ok = ok and recv2.shape[0] == 0 and int(counts2.sum()) == 0
+        # an exchange in which nobody travels still works (zero headers)
+        recv2 = x.exchange(torch.zeros((world, stride, REC_WORDS), dtype=torch.int32))
+        ok = ok and int(recv2[:, 0, 0].sum()) == 0
         ret[rank] = bool(ok)
     finally:
         dist.destroy_process_group()

@@ -41,7 +41,7 @@ def test_three_regions_commute_and_migration_bit_exact():
     engines, orc = build(R, kw, 31, plan, 600)
     try:
         assert_regions_equal(engines, orc, "init")
-        m = MultiRegion(engines, plan, max_records=4096)
+        m = MultiRegion(engines, plan, stride_records=512)
         hour = 1
         for day in range(7):
             rows = m.run(hour, 24)
@@ -63,7 +63,7 @@ def test_commute_only_hour_by_hour_state():
     plan = dict(n_regions=R, commute=np.array([[0, 120], [80, 0]], np.uint32))
     engines, orc = build(R, kw, 77, plan, 400)
     try:
-        m = MultiRegion(engines, plan, max_records=2048)
+        m = MultiRegion(engines, plan, stride_records=512)
         for hour in range(1, 24 * 3 + 1):
             rows = m.run(hour, 1)
             want = orc.step(hour)
@@ -88,9 +88,49 @@ def test_out_of_slots_is_an_error_not_a_crash():
     plan = dict(n_regions=R, commute=np.array([[0, 50], [0, 0]], np.uint32))
     engines, _ = build(R, kw, 5, plan, 10)
     try:
-        m = MultiRegion(engines, plan, max_records=1024)
+        m = MultiRegion(engines, plan, stride_records=256)
         with pytest.raises(EpiError, match="out of agent slots"):
             m.run(1, 8)
+    finally:
+        for e in engines:
+            e.close()
+
+
+def test_segment_overflow_is_reported():
+    from epirust_b200.engine import EpiError
+
+    R = 2
+    kw = dict(n_agents=2000, grid_size=160, hours=100, exposed=10)
+    plan = dict(n_regions=R, commute=np.array([[0, 50], [0, 0]], np.uint32))
+    engines, _ = build(R, kw, 5, plan, 200)
+    try:
+        m = MultiRegion(engines, plan, stride_records=16)  # 50 commuters do not fit a 15-record segment
+        with pytest.raises(EpiError, match="stride_records"):
+            m.run(1, 8)
+    finally:
+        for e in engines:
+            e.close()
+
+
+def test_many_migrators_fill_houses_level_by_level():
+    """A heavy migration plan: thousands of arrivals per exchange exercise the parallel water filling of the occupancy heaps
+    over several occupancy levels (houses hold at most 4), against the oracle's sequential BinaryHeap."""
+    R = 2
+    kw = dict(n_agents=6000, grid_size=200, hours=200, exposed=50, working=0.6)
+    plan = dict(n_regions=R, migration=np.array([[0, 2500], [100, 0]], np.uint32), start_migration_hour=10, end_migration_hour=60)
+    engines, orc = build(R, kw, 13, plan, 6000)
+    try:
+        m = MultiRegion(engines, plan, stride_records=4096)
+        hour = 1
+        for day in range(3):
+            rows = m.run(hour, 24)
+            for k in range(24):
+                want = orc.step(hour + k)
+                for r in range(R):
+                    assert (rows[r, k] == want[r]).all(), f"hour {hour + k} region {r}: gpu {rows[r, k]} oracle {want[r]}"
+            hour += 24
+            assert_regions_equal(engines, orc, f"end of day {day}")
+        assert engines[1].population > 6000 + 4000  # two exchanges of ~2500 arrivals: the 2000 one-resident houses fill first, then level 2
     finally:
         for e in engines:
             e.close()
