@@ -331,7 +331,7 @@ int alloc_travel(epi_engine* e, const epi_travel_plan* plan) {
     if ((rc = travel_alloc(e, &T.pref_office, nbo * OFFICE_CAP))) return rc;
     if ((rc = travel_alloc(e, &T.plan_house, 1))) return rc;
     if ((rc = travel_alloc(e, &T.plan_office, 1))) return rc;
-    if ((rc = travel_alloc(e, &e->t_block_counts, (size_t)(e->P.n + 255) / 256 + 1))) return rc;
+    if ((rc = travel_alloc(e, &e->t_block_counts, (size_t)(e->P.n + 1023) / 1024 + 1 + ((size_t)(e->P.n + 1023) / 1024) * 32))) return rc;  // block counts | warp ballots
     CU(cudaMallocHost((void**)&e->h_tv, sizeof(epi::TravelVars)));
     CU(cudaMemsetAsync(T.tv, 0, sizeof(epi::TravelVars), e->stream));
     CU(cudaMemcpyAsync(row, e->migration_row.data(), R * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
@@ -343,7 +343,10 @@ int alloc_travel(epi_engine* e, const epi_travel_plan* plan) {
 int reset_travel_state(epi_engine* e) {
     e->population = e->cfg.number_of_agents;
     if (!e->multi) return EPI_OK;
-    e->n_free = (uint32_t)e->free_stack0.size();
+    e->pack_unsettled = e->unpack_unsettled = false;
+    const uint32_t top = (uint32_t)e->free_stack0.size();
+    CU(cudaMemsetAsync(e->T.tv, 0, sizeof(epi::TravelVars), e->stream));
+    CU(cudaMemcpyAsync(&e->T.tv->free_top, &top, sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
     CU(cudaMemcpyAsync(e->T.free_stack, e->free_stack0.data(), e->free_stack0.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
     CU(cudaMemcpyAsync(e->T.occ_house, e->occ_house0.data(), e->occ_house0.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
     CU(cudaMemcpyAsync(e->T.occ_office, e->occ_office0.data(), e->occ_office0.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
@@ -575,6 +578,23 @@ int epi_step(epi_engine* e, uint32_t hour, epi_counts* out) {
     if (!e || !out) return engine_fail(e, EPI_ERR_ARG, "null argument");
     CU(cudaSetDevice(e->device));
     return run_chunk(e, hour, 1, false, out);
+}
+
+int epi_enqueue_hour(epi_engine* e, uint32_t hour) {
+    if (!e) return engine_fail(e, EPI_ERR_ARG, "null engine");
+    CU(cudaSetDevice(e->device));
+    CU(cudaMemsetAsync(e->D.counts, 0, 8 * sizeof(uint32_t), e->stream));
+    int rc = ensure_epoch(e, hour, hour);
+    if (rc) return rc;
+    {
+        Timed t(e, KK_MISC);
+        launch_set_clock(e->d_clock, Clock{hour, e->epoch_base, hour, 0}, e->stream);
+    }
+    rc = enqueue_hour(e, hour, 0, false, false);
+    if (rc) return rc;
+    e->have_last_row = false;
+    CU(cudaGetLastError());
+    return EPI_OK;
 }
 
 int epi_step_with_draws(epi_engine* e, uint32_t hour, const uint64_t* draws, epi_counts* out) {

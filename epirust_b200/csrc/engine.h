@@ -54,7 +54,9 @@ struct epi_engine {
     // The reference's sequential bookkeeping of the exchange lives on the device (travel.cu): the free-slot stack (LIFO: arrivals
     // pop, departures push) and the house / office occupancy heaps (grid.rs:47-80, 279-341) as occupancy arrays in tie order.
     // The host keeps the stack height and the initial images for epi_reset.
-    uint32_t n_free = 0;
+    bool pack_unsettled = false, unpack_unsettled = false;  // a deferred epi_travel_pack / unpack awaits its host-side settlement
+    epi::TravelArgs unpack_args{};
+    uint32_t unpack_attempt = 0, unpack_max_arrivals = 0;
     std::vector<uint32_t> free_stack0, occ_house0, occ_office0;
     uint32_t* i_reg = nullptr;
     epi::TravelPtrs T{};

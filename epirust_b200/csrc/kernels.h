@@ -17,9 +17,10 @@ void launch_vaccinate(const Params& P, const DevPtrs& D, uint64_t thr, uint32_t 
 void launch_build_grid(const Params& P, const DevPtrs& D, uint32_t* collisions, cudaStream_t s);
 // travel.cu (each returns the number of kernels it launched)
 unsigned launch_travel_leave(const Params& P, const DevPtrs& D, const TravelArgs& A, const TravelPtrs& T, uint32_t* block_counts, TravelRecord* send,
-                             uint32_t stride, uint32_t free_top, cudaStream_t s);
+                             uint32_t stride, cudaStream_t s);
 unsigned launch_travel_arrive(const Params& P, const DevPtrs& D, const TravelArgs& A, const TravelPtrs& T, const TravelRecord* recv, uint32_t stride,
-                              uint32_t n_in, uint32_t max_segment, uint32_t n_houses, uint32_t n_offices, uint32_t free_top, cudaStream_t s);
-unsigned launch_travel_rounds(const Params& P, const DevPtrs& D, const TravelArgs& A, const TravelPtrs& T, uint32_t n_in, uint32_t first_attempt, uint32_t n_rounds,
-                              uint32_t free_top, cudaStream_t s);
+                              uint32_t max_arrivals, uint32_t n_houses, uint32_t n_offices, cudaStream_t s);
+unsigned launch_travel_rounds(const Params& P, const DevPtrs& D, const TravelArgs& A, const TravelPtrs& T, uint32_t max_arrivals, uint32_t first_attempt, uint32_t n_rounds,
+                              cudaStream_t s);
+void launch_travel_arrivals_done(const TravelPtrs& T, cudaStream_t s);
 }  // namespace epi

@@ -128,7 +128,7 @@ constexpr uint32_t OCC_ABSENT = 0xFFFFFFFFu;  // a house / office that is not in
 constexpr uint32_t HOUSE_CAP = 4, OFFICE_CAP = 100;  // HOME_SIZE^2, OFFICE_SIZE^2 (constants.rs:45-46)
 enum : uint32_t {
     TERR_LIST_OVERFLOW = 1, TERR_SEGMENT_OVERFLOW = 2, TERR_NO_HOUSE = 4, TERR_NO_OFFICE = 8, TERR_HOUSES_FULL = 16, TERR_OFFICES_FULL = 32,
-    TERR_BAD_REGION = 64,
+    TERR_BAD_REGION = 64, TERR_NO_SLOTS = 128,
 };
 // scalars of one exchange; the host reads them back once per pack / unpack
 struct TravelVars {
@@ -137,7 +137,9 @@ struct TravelVars {
     uint32_t n_working;  // arriving migrators that take an office
     uint32_t pending;    // arrivals still without a cell after the placement rounds so far
     uint32_t err;        // TERR_* flags
-    uint32_t pad[3];
+    uint32_t n_in;       // arrivals of the exchange being unpacked
+    uint32_t free_top;   // height of the free-slot stack
+    uint32_t pad;
     uint32_t cnt[TRAVEL_MAX_REGIONS];   // records per destination region
     uint32_t base[TRAVEL_MAX_REGIONS];  // exclusive prefix of cnt
 };

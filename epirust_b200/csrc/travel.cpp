@@ -26,6 +26,18 @@ void note_launch(epi_engine* e, unsigned n = 1) {
     e->kernel_launches[KK_TRAVEL] += n;
 }
 
+// CUDA events around a group of travel kernels when per-kernel timing is on (epi_set_kernel_timing)
+struct TimedGroup {
+    epi_engine* e;
+    cudaEvent_t a = nullptr, b = nullptr;
+    explicit TimedGroup(epi_engine* e_) : e(e_) {
+        if (e->timing) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, e->stream); }
+    }
+    ~TimedGroup() {
+        if (e->timing) { cudaEventRecord(b, e->stream); e->pending_events.push_back({KK_TRAVEL, {a, b}}); }
+    }
+};
+
 std::string travel_error(uint32_t err) {
     std::string m;
     auto add = [&](uint32_t bit, const char* text) { if (err & bit) { if (!m.empty()) m += "; "; m += text; } };
@@ -46,18 +58,48 @@ int write_empty_headers(epi_engine* e, void* send_buf, uint64_t stride) {
     return EPI_OK;
 }
 
+// What a deferred pack / unpack left for the host to settle (epi_finish_hour or the next synchronous call does it)
+int settle_exchange(epi_engine* e) {
+    if (!e->pack_unsettled && !e->unpack_unsettled) return EPI_OK;
+    const uint32_t R = (uint32_t)e->n_regions;
+    for (;;) {
+        CU(cudaMemcpyAsync(e->h_tv, e->T.tv, (8 + R) * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaStreamSynchronize(e->stream));
+        CU(cudaGetLastError());
+        const uint32_t err = e->h_tv->err;
+        if (err & TERR_NO_SLOTS) return engine_fail(e, EPI_ERR_STATE, "region is out of agent slots: raise extra_capacity");
+        if (err) return engine_fail(e, EPI_ERR_STATE, "traveller exchange: " + travel_error(err));
+        if (!e->unpack_unsettled || e->h_tv->pending == 0) break;
+        // select_starting_points: more placement rounds until every arrival holds a distinct vacant cell
+        if (e->unpack_attempt > 64) return engine_fail(e, EPI_ERR_STATE, "Not enough locations are available for travellers");
+        TimedGroup t(e);
+        note_launch(e, launch_travel_rounds(e->P, e->D, e->unpack_args, e->T, e->unpack_max_arrivals, e->unpack_attempt, 4, e->stream));
+        e->unpack_attempt += 4;
+    }
+    if (e->pack_unsettled) e->population -= e->h_tv->n_send;
+    if (e->unpack_unsettled) {
+        e->population += e->h_tv->n_in;
+        launch_travel_arrivals_done(e->T, e->stream);  // the arrivals' slots leave the free stack
+        note_launch(e);
+    }
+    e->pack_unsettled = e->unpack_unsettled = false;
+    return EPI_OK;
+}
+
 }  // namespace
 
 extern "C" {
 
 int epi_travel_pack(epi_engine* e, uint32_t hour, int kind, void* send_buf, uint64_t stride_records, uint32_t* counts_out) {
-    if (!e || !counts_out) return engine_fail(e, EPI_ERR_ARG, "null argument");
+    if (!e) return engine_fail(e, EPI_ERR_ARG, "null argument");
     if (!e->multi) return engine_fail(e, EPI_ERR_STATE, "not a multi-region engine (epi_create_multi)");
     if (kind != TRAVEL_MIGRATE && kind != TRAVEL_COMMUTE) return engine_fail(e, EPI_ERR_ARG, "epi_travel_pack: kind must be EPI_TRAVEL_MIGRATE or EPI_TRAVEL_COMMUTE");
     if (!send_buf || stride_records < 2 || stride_records > 0xFFFFFFFFull) return engine_fail(e, EPI_ERR_ARG, "epi_travel_pack: send buffer / stride_records");
     const uint32_t R = (uint32_t)e->n_regions, h = hour % 24u;
-    std::fill(counts_out, counts_out + R, 0u);
+    if (counts_out) std::fill(counts_out, counts_out + R, 0u);
     CU(cudaSetDevice(e->device));
+    int rc = settle_exchange(e);  // an earlier deferred exchange (its epi_finish_hour was skipped)
+    if (rc) return rc;
     TravelArgs A{};
     A.kind = kind;
     A.hour = hour;
@@ -73,17 +115,16 @@ int epi_travel_pack(epi_engine* e, uint32_t hour, int kind, void* send_buf, uint
         return write_empty_headers(e, send_buf, stride_records);
     }
     CU(cudaMemsetAsync(&e->T.tv->err, 0, sizeof(uint32_t), e->stream));
-    note_launch(e, launch_travel_leave(e->P, e->D, A, e->T, e->t_block_counts, (TravelRecord*)send_buf, (uint32_t)stride_records, e->n_free, e->stream));
-    CU(cudaMemcpyAsync(e->h_tv, e->T.tv, sizeof(TravelVars), cudaMemcpyDeviceToHost, e->stream));
-    CU(cudaStreamSynchronize(e->stream));
-    CU(cudaGetLastError());
-    if (e->h_tv->err) return engine_fail(e, EPI_ERR_STATE, "epi_travel_pack: " + travel_error(e->h_tv->err));
-    const uint32_t n_send = e->h_tv->n_send;
-    for (uint32_t to = 0; to < R; ++to) counts_out[to] = e->h_tv->cnt[to];
-    // the leavers' slots went onto the free stack (remove_migrators / remove_commuters, allocation_map.rs:165-212)
-    e->n_free += n_send;
-    e->population -= n_send;
+    {
+        TimedGroup t(e);
+        note_launch(e, launch_travel_leave(e->P, e->D, A, e->T, e->t_block_counts, (TravelRecord*)send_buf, (uint32_t)stride_records, e->stream));
+    }
     e->have_last_row = false;
+    e->pack_unsettled = true;
+    if (!counts_out) return EPI_OK;  // deferred: the records are in flight on the stream, the host settles later
+    rc = settle_exchange(e);
+    if (rc) return rc;
+    for (uint32_t to = 0; to < R; ++to) counts_out[to] = e->h_tv->cnt[to];  // still the leavers' counts: no unpack ran in between
     return EPI_OK;
 }
 
@@ -94,52 +135,41 @@ int epi_travel_unpack(epi_engine* e, uint32_t hour, int kind, const void* recv_b
     if (!recv_buf || stride_records < 2 || stride_records > 0xFFFFFFFFull) return engine_fail(e, EPI_ERR_ARG, "epi_travel_unpack: receive buffer / stride_records");
     const uint32_t R = (uint32_t)e->n_regions, stride = (uint32_t)stride_records;
     CU(cudaSetDevice(e->device));
-    // the segment headers: records per source region
-    std::vector<uint32_t> heads(R);
-    uint32_t* h_heads = R <= 64 ? e->h_small : heads.data();
-    CU(cudaMemcpy2DAsync(h_heads, sizeof(uint32_t), recv_buf, (size_t)stride * sizeof(TravelRecord), sizeof(uint32_t), R, cudaMemcpyDeviceToHost, e->stream));
-    CU(cudaStreamSynchronize(e->stream));
-    uint64_t n64 = 0;
-    uint32_t max_segment = 0;
-    for (uint32_t r = 0; r < R; ++r) {
-        const uint32_t c = std::min(h_heads[r], stride - 1u);
-        if (counts_in) counts_in[r] = c;
-        n64 += c;
-        max_segment = std::max(max_segment, c);
+    if (e->unpack_unsettled) {
+        const int rc = settle_exchange(e);
+        if (rc) return rc;
     }
-    if (n64 == 0) return EPI_OK;
-    const uint32_t n_in = (uint32_t)n64;
-    if (e->n_free < n_in) return engine_fail(e, EPI_ERR_STATE, "region is out of agent slots: raise extra_capacity (" + std::to_string(n_in) + " arrivals)");
-    if (n_in > e->T.list_cap) return engine_fail(e, EPI_ERR_STATE, "more arrivals than the exchange lists hold (" + std::to_string(n_in) + ")");
-    TravelArgs A{};
+    // The number of arrivals is only known on the device (the segment headers); the kernels read it there and the grids are
+    // sized for the most this region can take, so the host need not synchronise before the placement rounds have run.
+    e->unpack_max_arrivals = (uint32_t)std::min<uint64_t>(e->T.list_cap, (uint64_t)R * (stride - 1u));
+    TravelArgs& A = e->unpack_args;
+    A = TravelArgs{};
     A.kind = kind;
     A.hour = hour;
     A.hour_of_day = hour % 24u;
-    CU(cudaMemsetAsync(&e->T.tv->err, 0, sizeof(uint32_t), e->stream));
-    CU(cudaMemsetAsync(e->T.placed, 0, n_in, e->stream));
-    note_launch(e, launch_travel_arrive(e->P, e->D, A, e->T, (const TravelRecord*)recv_buf, stride, n_in, max_segment, e->geo.n_houses, e->geo.n_offices, e->n_free, e->stream));
-    // select_starting_points: placement rounds until every arrival holds a distinct vacant cell; the host looks at the count of
-    // unplaced arrivals only every few rounds
-    for (uint32_t attempt = 0;;) {
-        const uint32_t rounds = attempt == 0 ? 3u : 4u;
-        note_launch(e, launch_travel_rounds(e->P, e->D, A, e->T, n_in, attempt, rounds, e->n_free, e->stream));
-        attempt += rounds;
-        CU(cudaMemcpyAsync(e->h_tv, e->T.tv, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
-        CU(cudaStreamSynchronize(e->stream));
-        if (e->h_tv->err) return engine_fail(e, EPI_ERR_STATE, "epi_travel_unpack: " + travel_error(e->h_tv->err));
-        if (e->h_tv->pending == 0) break;
-        if (attempt > 64) return engine_fail(e, EPI_ERR_STATE, "Not enough locations are available for travellers");
+    if (!e->pack_unsettled) CU(cudaMemsetAsync(&e->T.tv->err, 0, sizeof(uint32_t), e->stream));
+    {
+        TimedGroup t(e);
+        note_launch(e, launch_travel_arrive(e->P, e->D, A, e->T, (const TravelRecord*)recv_buf, stride, e->unpack_max_arrivals, e->geo.n_houses, e->geo.n_offices, e->stream));
+        note_launch(e, launch_travel_rounds(e->P, e->D, A, e->T, e->unpack_max_arrivals, 0, 3, e->stream));
     }
-    e->n_free -= n_in;
-    e->population += n_in;
+    e->unpack_attempt = 3;
+    e->unpack_unsettled = true;
     e->have_last_row = false;
-    CU(cudaGetLastError());
+    if (!counts_in) return EPI_OK;  // deferred
+    const int rc = settle_exchange(e);
+    if (rc) return rc;
+    for (uint32_t r = 0; r < R; ++r) counts_in[r] = e->h_tv->cnt[r];
     return EPI_OK;
 }
 
 int epi_finish_hour(epi_engine* e, uint32_t hour, epi_counts* out) {
     if (!e || !out) return engine_fail(e, EPI_ERR_ARG, "null argument");
     CU(cudaSetDevice(e->device));
+    {
+        const int rc = settle_exchange(e);
+        if (rc) return rc;
+    }
     // Counts after remove_* / assimilate_* adjusted them: the running totals on the device
     std::vector<uint32_t> tot((size_t)TOT_COPIES * 8);
     CU(cudaMemcpyAsync(tot.data(), e->D.tot, tot.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));

@@ -97,9 +97,15 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* w
 }
 
 // ---- leaving ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_travel_flag_count(Params P, DevPtrs D, TravelArgs A, uint32_t* __restrict__ block_counts) {
+// Ordered compaction of the leaving candidates.  Pass 1 evaluates the flag of every slot once, keeps the warp ballots and
+// counts per block of 1024 slots; one block scans the counts; pass 2 places the flagged slots from the ballots (it reads
+// reg[] again only for the few flagged agents).
+constexpr uint32_t SEL_BLOCK = 1024;
+__global__ void __launch_bounds__(SEL_BLOCK) k_travel_flag_count(Params P, DevPtrs D, TravelArgs A, uint32_t* __restrict__ block_counts, uint32_t* __restrict__ ballots) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t f = i < P.n ? travel_flag(P, A, i, D.st[i], D.reg[i]) : 0u;
+    const unsigned b = __ballot_sync(0xFFFFFFFFu, f != 0);
+    if ((threadIdx.x & 31u) == 0) ballots[i >> 5] = b;
     const int n = __syncthreads_count(f != 0);
     if (threadIdx.x == 0) block_counts[blockIdx.x] = (uint32_t)n;
 }
@@ -122,21 +128,26 @@ __global__ void __launch_bounds__(1024) k_travel_scan(uint32_t* __restrict__ blo
     }
 }
 
-__global__ void __launch_bounds__(256) k_travel_scatter(Params P, DevPtrs D, TravelArgs A, TravelPtrs T, const uint32_t* __restrict__ block_offsets) {
-    __shared__ uint32_t warp_counts[8];
+__global__ void __launch_bounds__(SEL_BLOCK) k_travel_scatter(Params P, DevPtrs D, TravelArgs A, TravelPtrs T, const uint32_t* __restrict__ block_offsets,
+                                                               const uint32_t* __restrict__ ballots) {
+    __shared__ uint32_t warp_sums[32];
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t f = i < P.n ? travel_flag(P, A, i, D.st[i], D.reg[i]) : 0u;
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const unsigned b = __ballot_sync(0xFFFFFFFFu, f != 0);
-    if (lane == 0) warp_counts[warp] = (uint32_t)__popc(b);
-    __syncthreads();
-    if (f) {
-        uint32_t rank = __popc(b & ((1u << lane) - 1u));
-        for (unsigned w = 0; w < warp; ++w) rank += warp_counts[w];
-        const uint32_t at = block_offsets[blockIdx.x] + rank;
+    const unsigned b = ballots[i >> 5];  // written for every warp of the launch, also beyond P.n
+    uint32_t total;
+    const uint32_t before = block_exclusive_scan(lane == 0 ? (uint32_t)__popc(b) : 0u, warp_sums, &total);  // lane 0 holds the flagged slots in earlier warps
+    const uint32_t warp_base = __shfl_sync(0xFFFFFFFFu, before, 0);
+    (void)warp;
+    if ((b >> lane) & 1u) {
+        const uint32_t at = block_offsets[blockIdx.x] + warp_base + (uint32_t)__popc(b & ((1u << lane) - 1u));
         if (at < T.list_cap) {
             T.list_slot[at] = i;
-            T.list_dest[at] = f - 1u;
+            uint32_t dest = 0;
+            if (A.kind == TRAVEL_COMMUTE) {  // Citizen::is_commuter: the work region in the morning, the home region in the evening
+                const uint32_t reg = D.reg[i];
+                dest = A.hour_of_day == 7u ? (reg >> 8) & 0xFFu : reg & 0xFFu;
+            }
+            T.list_dest[at] = dest;
         } else atomicOr(&T.tv->err, TERR_LIST_OVERFLOW);
     }
 }
@@ -207,10 +218,10 @@ __global__ void __launch_bounds__(1024) k_travel_rank(TravelPtrs T) {
 
 // the agent leaves: record written, cell vacated, slot emptied and pushed, Counts decremented (decrement_counts,
 // allocation_map.rs:291-301), occupancies of its house / office decremented (remove_migrators, :165-192)
-__global__ void __launch_bounds__(256) k_travel_pack(Params P, DevPtrs D, TravelArgs A, TravelPtrs T, TravelRecord* __restrict__ send, uint32_t stride,
-                                                      uint32_t free_top) {
+__global__ void __launch_bounds__(256) k_travel_pack(Params P, DevPtrs D, TravelArgs A, TravelPtrs T, TravelRecord* __restrict__ send, uint32_t stride) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     TravelVars* tv = T.tv;
+    const uint32_t free_top = tv->free_top;
     const uint32_t total = min(tv->total, T.list_cap);
     if (p >= total) return;
     uint32_t dest, j;
@@ -245,21 +256,44 @@ __global__ void __launch_bounds__(256) k_travel_pack(Params P, DevPtrs D, Travel
     }
 }
 
+// the free-slot stack grows by the leavers (after k_travel_pack) / shrinks by the arrivals (after the last placement round)
+__global__ void k_travel_stack_moved(TravelVars* tv, int arrivals) {
+    if (arrivals) tv->free_top -= tv->n_in;
+    else tv->free_top += tv->n_send;
+}
+
 // ---- arriving -----------------------------------------------------------------------------------------------------------
 // recv: one segment per source region (header + records) -> arrivals[k], k ascending in (source region, index)
-__global__ void __launch_bounds__(256) k_travel_gather(TravelPtrs T, const TravelRecord* __restrict__ recv, uint32_t stride, int kind) {
+// n_in = the sum of the segment headers (tv->cnt[s] keeps the header of source s for the host)
+__global__ void __launch_bounds__(256) k_travel_count_in(TravelPtrs T, const TravelRecord* __restrict__ recv, uint32_t stride) {
+    if (threadIdx.x != 0) return;
+    const uint32_t free_top = T.tv->free_top;
+    uint32_t n = 0;
+    for (int s = 0; s < T.n_regions; ++s) {
+        const uint32_t c = min(recv[(size_t)s * stride].st, stride - 1u);
+        T.tv->cnt[s] = c;
+        n += c;
+    }
+    if (n > T.list_cap) { atomicOr(&T.tv->err, TERR_LIST_OVERFLOW); n = 0; }
+    if (n > free_top) { atomicOr(&T.tv->err, TERR_NO_SLOTS); n = 0; }  // "region is out of agent slots"
+    T.tv->n_in = n;
+    T.tv->n_working = 0;
+    T.tv->pending = 0;
+}
+__global__ void __launch_bounds__(256) k_travel_gather(TravelPtrs T, const TravelRecord* __restrict__ recv, uint32_t stride) {
     const uint32_t s = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t cnt = min(recv[(size_t)s * stride].st, stride - 1u);
-    if (j >= cnt) return;
+    if (T.tv->n_in == 0) return;
+    if (j >= T.tv->cnt[s]) return;
     uint32_t k = j;
-    for (uint32_t q = 0; q < s; ++q) k += min(recv[(size_t)q * stride].st, stride - 1u);
-    if (k >= T.list_cap) { atomicOr(&T.tv->err, TERR_LIST_OVERFLOW); return; }
+    for (uint32_t q = 0; q < s; ++q) k += T.tv->cnt[q];
     T.arrivals[k] = recv[(size_t)s * stride + 1u + j];
+    T.placed[k] = 0;
 }
 
 // migrators: arr_widx[k] = number of working arrivals before k; tv->n_working = their total (they pop an office each)
-__global__ void __launch_bounds__(1024) k_travel_wscan(TravelPtrs T, uint32_t n_in) {
+__global__ void __launch_bounds__(1024) k_travel_wscan(TravelPtrs T) {
     __shared__ uint32_t warp_sums[32];
+    const uint32_t n_in = T.tv->n_in;
     uint32_t carry = 0;
     for (uint32_t base = 0; base < n_in; base += 1024u) {
         const uint32_t k = base + threadIdx.x;
@@ -280,27 +314,36 @@ __global__ void __launch_bounds__(256) k_occ_block_hist(const uint32_t* __restri
     for (uint32_t l = threadIdx.x; l < CAP; l += blockDim.x) h[l] = 0;
     __syncthreads();
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r < n) {
-        const uint32_t o = occ[r];
-        if (o < CAP) atomicAdd(&h[o], 1u);
-    }
+    const uint32_t o = r < n ? occ[r] : OCC_ABSENT;
+    if (CAP <= 8) {  // few levels: block-wide counts instead of shared atomics on a handful of addresses
+#pragma unroll
+        for (uint32_t l = 0; l < CAP; ++l) {
+            const int c = __syncthreads_count(o == l);
+            if (threadIdx.x == 0) h[l] = (uint32_t)c;
+        }
+    } else if (o < CAP) atomicAdd(&h[o], 1u);
     __syncthreads();
     for (uint32_t l = threadIdx.x; l < CAP; l += blockDim.x) bh[(size_t)blockIdx.x * CAP + l] = h[l];
 }
 // the level structure of K pops.  k_src: K is read from *k_src when non-null (a device-side count), else k_arg.
 template <uint32_t CAP>
-__global__ void __launch_bounds__(1024) k_occ_plan(const uint32_t* __restrict__ bh, uint32_t n_blocks, FillPlan* __restrict__ plan, const uint32_t* k_src, uint32_t k_arg,
+__global__ void __launch_bounds__(1024) k_occ_plan(const uint32_t* __restrict__ bh, uint32_t n_blocks, FillPlan* __restrict__ plan, const uint32_t* k_src,
                                                     TravelVars* tv, uint32_t err_bit) {
     __shared__ uint32_t H[CAP];
     for (uint32_t l = threadIdx.x; l < CAP; l += blockDim.x) H[l] = 0;
     __syncthreads();
-    for (uint32_t idx = threadIdx.x; idx < n_blocks * CAP; idx += blockDim.x) {
-        const uint32_t v = bh[idx];
-        if (v) atomicAdd(&H[idx % CAP], v);
+    {   // thread t sums level t % CAP over the blocks t / CAP, t / CAP + groups, ...
+        const uint32_t groups = 1024u / CAP;
+        if (threadIdx.x < groups * CAP) {
+            const uint32_t l = threadIdx.x % CAP;
+            uint32_t sum = 0;
+            for (uint32_t b = threadIdx.x / CAP; b < n_blocks; b += groups) sum += bh[(size_t)b * CAP + l];
+            if (sum) atomicAdd(&H[l], sum);
+        }
     }
     __syncthreads();
     if (threadIdx.x != 0) return;
-    const uint32_t K = k_src ? *k_src : k_arg;
+    const uint32_t K = *k_src;
     plan->K = K; plan->L = 0; plan->l_last = 0; plan->last_count = 0;
     if (K == 0) return;
     uint32_t L = 0;
@@ -337,14 +380,18 @@ __global__ void __launch_bounds__(1024) k_occ_prefix(const uint32_t* __restrict_
         carry += sum;
     }
 }
-// pop p -> the area it returns (index in tie order)
+// pop p -> the area it returns (index in tie order).  One warp per arrival.
 template <uint32_t CAP>
 __global__ void __launch_bounds__(256) k_occ_assign(const uint32_t* __restrict__ occ, uint32_t n, uint32_t n_blocks, const FillPlan* __restrict__ plan,
-                                                     const uint32_t* __restrict__ pref, uint32_t* __restrict__ out, const uint32_t* __restrict__ pop_index, uint32_t n_arrivals) {
-    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n_arrivals) return;
+                                                     const uint32_t* __restrict__ pref, uint32_t* __restrict__ out, const uint32_t* __restrict__ pop_index,
+                                                     const uint32_t* __restrict__ n_arrivals) {
+    const uint32_t k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+    if (k >= *n_arrivals) return;
     const uint32_t p = pop_index ? pop_index[k] : k;  // which pop of this heap serves arrival k (0xFFFFFFFF: none)
-    if (p >= plan->K) { out[k] = 0xFFFFFFFFu; return; }
+    if (p >= plan->K) {
+        if (lane == 0) out[k] = 0xFFFFFFFFu;
+        return;
+    }
     uint32_t l = plan->L;
     while (l < plan->l_last && p >= plan->start[l + 1]) ++l;
     const uint32_t q = p - plan->start[l];
@@ -354,15 +401,22 @@ __global__ void __launch_bounds__(256) k_occ_assign(const uint32_t* __restrict__
         const uint32_t mid = (lo + hi) >> 1;
         if (pl[mid] <= q) lo = mid; else hi = mid;
     }
-    uint32_t left = q - pl[lo];
-    uint32_t r = lo * 256u;
-    const uint32_t end = min(r + 256u, n);
-    for (; r < end; ++r)
-        if (occ[r] <= l) {
-            if (left == 0) break;
-            --left;
+    uint32_t left = q - pl[lo];  // the left-th area with occupancy <= l inside block lo (256 areas)
+    uint32_t found = 0xFFFFFFFFu;
+    for (uint32_t c = 0; c < 8; ++c) {
+        const uint32_t r = lo * 256u + c * 32u + lane;
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, r < n && occ[r] <= l);
+        const uint32_t cnt = (uint32_t)__popc(m);
+        if (left < cnt) {
+            // position of the left-th set bit of m
+            unsigned mm = m;
+            for (uint32_t t = 0; t < left; ++t) mm &= mm - 1u;
+            found = lo * 256u + c * 32u + (uint32_t)(__ffs(mm) - 1);
+            break;
         }
-    out[k] = r;
+        left -= cnt;
+    }
+    if (lane == 0) out[k] = found;
 }
 // every area that was popped comes back with one more occupant per pop
 template <uint32_t CAP>
@@ -384,9 +438,10 @@ __global__ void __launch_bounds__(256) k_occ_update(uint32_t* __restrict__ occ, 
 // immunity, vaccinated, uses_public_transport and the disease state travel; hospitalized, isolated, work_quarantined reset;
 // work status becomes NA (migrator) or Normal (commuter); current_area = the housing strip.  The cell is assigned by the
 // placement rounds.
-__global__ void __launch_bounds__(256) k_travel_install(Params P, DevPtrs D, TravelArgs A, TravelPtrs T, uint32_t n_in, uint32_t free_top) {
+__global__ void __launch_bounds__(256) k_travel_install(Params P, DevPtrs D, TravelArgs A, TravelPtrs T) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n_in) return;
+    if (k >= T.tv->n_in) return;
+    const uint32_t free_top = T.tv->free_top;
     const TravelRecord r = T.arrivals[k];
     const uint32_t i = T.free_stack[free_top - 1u - k];
     const uint32_t keep = ST_STATE_MASK | (3u << ST_SEV_SHIFT) | (7u << ST_IMM_SHIFT) | ST_VACC | ST_PT | (ST_DAY_MAX << ST_DAY_SHIFT);
@@ -439,9 +494,9 @@ __global__ void __launch_bounds__(256) k_travel_round_begin(TravelPtrs T) {
     if (idx <= T.table_mask) { T.table_keys[idx] = 0u; T.table_vals[idx] = 0xFFFFFFFFu; }
     if (idx == 0) T.tv->pending = 0;
 }
-__global__ void __launch_bounds__(256) k_travel_propose(Params P, DevPtrs D, TravelArgs A, TravelPtrs T, uint32_t n_in, uint32_t attempt) {
+__global__ void __launch_bounds__(256) k_travel_propose(Params P, DevPtrs D, TravelArgs A, TravelPtrs T, uint32_t attempt) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n_in || T.placed[k]) return;
+    if (k >= T.tv->n_in || T.placed[k]) return;
     const uint32_t c = first_vacant_candidate(P, D, A, k, attempt);
     T.list_pos[k] = c;  // this round's proposal (list_pos is free during unpack)
     if (c == 0xFFFFFFFFu) return;
@@ -452,9 +507,10 @@ __global__ void __launch_bounds__(256) k_travel_propose(Params P, DevPtrs D, Tra
         slot = (slot + 1u) & T.table_mask;
     }
 }
-__global__ void __launch_bounds__(256) k_travel_grant(Params P, DevPtrs D, TravelArgs A, TravelPtrs T, uint32_t n_in, uint32_t free_top) {
+__global__ void __launch_bounds__(256) k_travel_grant(Params P, DevPtrs D, TravelArgs A, TravelPtrs T) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n_in || T.placed[k]) return;
+    if (k >= T.tv->n_in || T.placed[k]) return;
+    const uint32_t free_top = T.tv->free_top;
     const uint32_t c = T.list_pos[k];
     bool won = false;
     if (c != 0xFFFFFFFFu) {
@@ -480,59 +536,63 @@ __global__ void __launch_bounds__(256) k_travel_grant(Params P, DevPtrs D, Trave
 static inline unsigned blocks_for(uint32_t n) { return (n + 255u) / 256u; }
 
 unsigned launch_travel_leave(const Params& P, const DevPtrs& D, const TravelArgs& A, const TravelPtrs& T, uint32_t* block_counts, TravelRecord* send,
-                             uint32_t stride, uint32_t free_top, cudaStream_t s) {
-    const unsigned nb = blocks_for(P.n);
-    k_travel_flag_count<<<nb, 256, 0, s>>>(P, D, A, block_counts);
+                             uint32_t stride, cudaStream_t s) {
+    const unsigned nb = (P.n + SEL_BLOCK - 1u) / SEL_BLOCK;
+    uint32_t* ballots = block_counts + nb + 1;  // the host allocates both in one array
+    k_travel_flag_count<<<nb, SEL_BLOCK, 0, s>>>(P, D, A, block_counts, ballots);
     k_travel_scan<<<1, 1024, 0, s>>>(block_counts, nb, T.tv);
-    k_travel_scatter<<<nb, 256, 0, s>>>(P, D, A, T, block_counts);
+    k_travel_scatter<<<nb, SEL_BLOCK, 0, s>>>(P, D, A, T, block_counts, ballots);
     k_travel_plan<<<1, 1024, 0, s>>>(P, A, T, send, stride);
-    unsigned launches = 5;
+    unsigned launches = 6;
     if (A.kind == TRAVEL_COMMUTE) { k_travel_rank<<<(unsigned)T.n_regions, 1024, 0, s>>>(T); ++launches; }
-    k_travel_pack<<<blocks_for(T.list_cap), 256, 0, s>>>(P, D, A, T, send, stride, free_top);
+    k_travel_pack<<<blocks_for(T.list_cap), 256, 0, s>>>(P, D, A, T, send, stride);
+    k_travel_stack_moved<<<1, 1, 0, s>>>(T.tv, 0);
     return launches;
 }
 
 template <uint32_t CAP>
-static unsigned water_fill(uint32_t* occ, uint32_t n, uint32_t* bh, uint32_t* pref, FillPlan* plan, const uint32_t* k_src, uint32_t k_arg, TravelVars* tv,
-                           uint32_t err_bit, uint32_t* out, const uint32_t* pop_index, uint32_t n_arrivals, cudaStream_t s) {
+static unsigned water_fill(uint32_t* occ, uint32_t n, uint32_t* bh, uint32_t* pref, FillPlan* plan, const uint32_t* k_src, TravelVars* tv, uint32_t err_bit, uint32_t* out,
+                           const uint32_t* pop_index, uint32_t max_arrivals, cudaStream_t s) {
     const unsigned nb = blocks_for(n);
     k_occ_block_hist<CAP><<<nb, 256, 0, s>>>(occ, n, bh);
-    k_occ_plan<CAP><<<1, 1024, 0, s>>>(bh, nb, plan, k_src, k_arg, tv, err_bit);
+    k_occ_plan<CAP><<<1, 1024, 0, s>>>(bh, nb, plan, k_src, tv, err_bit);
     k_occ_prefix<CAP><<<CAP, 1024, 0, s>>>(bh, nb, plan, pref);
-    k_occ_assign<CAP><<<blocks_for(n_arrivals), 256, 0, s>>>(occ, n, nb, plan, pref, out, pop_index, n_arrivals);
+    k_occ_assign<CAP><<<blocks_for(max_arrivals * 32u), 256, 0, s>>>(occ, n, nb, plan, pref, out, pop_index, &tv->n_in);
     k_occ_update<CAP><<<nb, 256, 0, s>>>(occ, n, nb, plan, pref);
     return 5;
 }
 
+// max_arrivals: upper bound of the arrivals (grid size); the kernels read the actual number from the segment headers
 unsigned launch_travel_arrive(const Params& P, const DevPtrs& D, const TravelArgs& A, const TravelPtrs& T, const TravelRecord* recv, uint32_t stride,
-                              uint32_t n_in, uint32_t max_segment, uint32_t n_houses, uint32_t n_offices, uint32_t free_top, cudaStream_t s) {
-    unsigned launches = 0;
-    k_travel_gather<<<dim3(blocks_for(max_segment), (unsigned)T.n_regions), 256, 0, s>>>(T, recv, stride, A.kind);
-    ++launches;
+                              uint32_t max_arrivals, uint32_t n_houses, uint32_t n_offices, cudaStream_t s) {
+    unsigned launches = 2;
+    k_travel_count_in<<<1, 32, 0, s>>>(T, recv, stride);
+    k_travel_gather<<<dim3(blocks_for(stride), (unsigned)T.n_regions), 256, 0, s>>>(T, recv, stride);
     if (A.kind == TRAVEL_MIGRATE) {
         // assimilate_migrators (allocation_map.rs:214-243): every arrival pops a house, the working ones an office as well
-        k_travel_wscan<<<1, 1024, 0, s>>>(T, n_in);
+        k_travel_wscan<<<1, 1024, 0, s>>>(T);
         ++launches;
-        launches += water_fill<HOUSE_CAP>(T.occ_house, n_houses, T.bh_house, T.pref_house, T.plan_house, nullptr, n_in, T.tv, TERR_HOUSES_FULL, T.arr_house, nullptr, n_in, s);
-        launches += water_fill<OFFICE_CAP>(T.occ_office, n_offices, T.bh_office, T.pref_office, T.plan_office, &T.tv->n_working, 0, T.tv, TERR_OFFICES_FULL, T.arr_office,
-                                           T.arr_widx, n_in, s);
+        launches += water_fill<HOUSE_CAP>(T.occ_house, n_houses, T.bh_house, T.pref_house, T.plan_house, &T.tv->n_in, T.tv, TERR_HOUSES_FULL, T.arr_house, nullptr, max_arrivals, s);
+        launches += water_fill<OFFICE_CAP>(T.occ_office, n_offices, T.bh_office, T.pref_office, T.plan_office, &T.tv->n_working, T.tv, TERR_OFFICES_FULL, T.arr_office, T.arr_widx,
+                                           max_arrivals, s);
     } else if (A.hour == 7u) {
         // assimilate_commuters (allocation_map.rs:245-277): an office is assigned at the absolute hour 7 only (:260)
-        launches += water_fill<OFFICE_CAP>(T.occ_office, n_offices, T.bh_office, T.pref_office, T.plan_office, nullptr, n_in, T.tv, TERR_OFFICES_FULL, T.arr_office, nullptr,
-                                           n_in, s);
+        launches += water_fill<OFFICE_CAP>(T.occ_office, n_offices, T.bh_office, T.pref_office, T.plan_office, &T.tv->n_in, T.tv, TERR_OFFICES_FULL, T.arr_office, nullptr,
+                                           max_arrivals, s);
     }
-    k_travel_install<<<blocks_for(n_in), 256, 0, s>>>(P, D, A, T, n_in, free_top);
+    k_travel_install<<<blocks_for(max_arrivals), 256, 0, s>>>(P, D, A, T);
     return launches + 1;
 }
 
-unsigned launch_travel_rounds(const Params& P, const DevPtrs& D, const TravelArgs& A, const TravelPtrs& T, uint32_t n_in, uint32_t first_attempt, uint32_t n_rounds,
-                              uint32_t free_top, cudaStream_t s) {
+unsigned launch_travel_rounds(const Params& P, const DevPtrs& D, const TravelArgs& A, const TravelPtrs& T, uint32_t max_arrivals, uint32_t first_attempt, uint32_t n_rounds,
+                              cudaStream_t s) {
     for (uint32_t a = 0; a < n_rounds; ++a) {
         k_travel_round_begin<<<blocks_for(T.table_mask + 1u), 256, 0, s>>>(T);
-        k_travel_propose<<<blocks_for(n_in), 256, 0, s>>>(P, D, A, T, n_in, first_attempt + a);
-        k_travel_grant<<<blocks_for(n_in), 256, 0, s>>>(P, D, A, T, n_in, free_top);
+        k_travel_propose<<<blocks_for(max_arrivals), 256, 0, s>>>(P, D, A, T, first_attempt + a);
+        k_travel_grant<<<blocks_for(max_arrivals), 256, 0, s>>>(P, D, A, T);
     }
     return 3 * n_rounds;
 }
+void launch_travel_arrivals_done(const TravelPtrs& T, cudaStream_t s) { k_travel_stack_moved<<<1, 1, 0, s>>>(T.tv, 1); }
 
 }  // namespace epi

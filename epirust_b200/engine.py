@@ -102,6 +102,7 @@ class Engine:
         if rc:
             raise EpiError(f"epi_create failed ({rc}): {self.L.epi_last_error(None).decode()}")
         self.h = h
+        self.stream_ptr = 0  # the engine's own stream
 
     def _check(self, rc):
         if rc:
@@ -133,15 +134,23 @@ class Engine:
         return self.L.epi_capacity(self.h)
 
     # ---- traveller exchange (multi-region engines) ----
-    def travel_pack(self, hour, kind, send_ptr, stride_records):
+    def travel_pack(self, hour, kind, send_ptr, stride_records, want_counts=True):
         """send_ptr: device pointer (int) of n_regions segments of stride_records records (segment d = header + the records for
-        region d).  Returns the per-destination record counts (host, numpy uint32[n_regions])."""
+        region d).  Returns the per-destination record counts (host, numpy uint32[n_regions]); with want_counts=False the call is
+        deferred (kernels in flight, settled by finish_hour) and returns None."""
+        if not want_counts:
+            self._check(self.L.epi_travel_pack(self.h, hour, kind, C.c_void_p(send_ptr), stride_records, None))
+            return None
         counts = np.zeros(self.n_regions, np.uint32)
         self._check(self.L.epi_travel_pack(self.h, hour, kind, C.c_void_p(send_ptr), stride_records, _ptr(counts)))
         return counts
 
-    def travel_unpack(self, hour, kind, recv_ptr, stride_records):
-        """recv_ptr: device pointer of n_regions segments (segment s = header + the records region s sent).  Returns counts per source."""
+    def travel_unpack(self, hour, kind, recv_ptr, stride_records, want_counts=True):
+        """recv_ptr: device pointer of n_regions segments (segment s = header + the records region s sent).  Returns counts per source
+        (None when deferred)."""
+        if not want_counts:
+            self._check(self.L.epi_travel_unpack(self.h, hour, kind, C.c_void_p(recv_ptr), stride_records, None))
+            return None
         counts_in = np.zeros(self.n_regions, np.uint32)
         self._check(self.L.epi_travel_unpack(self.h, hour, kind, C.c_void_p(recv_ptr), stride_records, _ptr(counts_in)))
         return counts_in
@@ -163,6 +172,11 @@ class Engine:
 
     def set_stream(self, cuda_stream_ptr):
         self._check(self.L.epi_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
+        self.stream_ptr = int(cuda_stream_ptr or 0)
+
+    def enqueue_hour(self, hour):
+        """CitizenLocationMap::simulate for one hour, asynchronously (no Counts row; see epi_finish_hour)."""
+        self._check(self.L.epi_enqueue_hour(self.h, hour))
 
     def sync(self):
         self._check(self.L.epi_sync(self.h))

@@ -29,6 +29,15 @@ def exchange_hours(plan):
     return kinds
 
 
+def exchange_kind(plan, kinds, hour):
+    """Kind of the exchange at `hour`, or None.  A migration hour outside the migration window moves nobody in any region
+    (Citizen::can_migrate, citizen/mod.rs:460-462), so every rank skips it alike."""
+    kind = kinds.get(hour % 24)
+    if kind == _ffi.TRAVEL_MIGRATE and not (int(plan.get("start_migration_hour", 0)) < hour < int(plan.get("end_migration_hour", 0))):
+        return None
+    return kind
+
+
 class DistExchange:
     """all-to-all over torch.distributed; `device` is the torch device of the record buffers.  The buffers are padded (one
     fixed-size segment per peer, the record count in the segment header), so ONE collective with equal splits moves counts
@@ -76,13 +85,16 @@ class MultiRegion:
 
     def next_exchange_hour(self, hour, last_hour):
         for h in range(hour, last_hour + 1):
-            if h % 24 in self.kinds:
+            if exchange_kind(self.plan, self.kinds, h) is not None:
                 return h
         return None
 
     def _do_exchange(self, hour, kind):
+        # Without a listener nothing on the host needs the counts: pack, collective and unpack are queued back to back on the
+        # stream and finish_hour settles the host side with one synchronisation.
+        deferred = self.on_outgoing is None
         for i, e in enumerate(self.engines):
-            counts = e.travel_pack(hour, kind, self.send[i].data_ptr(), self.stride)
+            counts = e.travel_pack(hour, kind, self.send[i].data_ptr(), self.stride, want_counts=not deferred)
             if self.on_outgoing is not None:
                 self.on_outgoing(hour, kind, self.send[i], counts)
         if self.exchange is None:
@@ -92,12 +104,15 @@ class MultiRegion:
             recv = self.send.transpose(0, 1).contiguous()
             torch.cuda.current_stream().synchronize()
             for r, e in enumerate(self.engines):
-                e.travel_unpack(hour, kind, recv[r].data_ptr(), self.stride)
+                e.travel_unpack(hour, kind, recv[r].data_ptr(), self.stride, want_counts=not deferred)
         else:
             (e,) = self.engines
+            if e.stream_ptr != torch.cuda.current_stream().cuda_stream:  # the collective runs on another stream than the engine's
+                e.sync()
             recv = self.exchange.exchange(self.send[0])
-            torch.cuda.current_stream().synchronize()
-            e.travel_unpack(hour, kind, recv.data_ptr(), self.stride)
+            if e.stream_ptr != torch.cuda.current_stream().cuda_stream:
+                torch.cuda.current_stream().synchronize()
+            e.travel_unpack(hour, kind, recv.data_ptr(), self.stride, want_counts=not deferred)
 
     def run(self, first_hour, n_hours, rows_out=None):
         """Hours first_hour .. first_hour + n_hours - 1 of every local region.  Returns rows[n_local, n_hours, 7]."""
@@ -112,10 +127,8 @@ class MultiRegion:
             if x is None:
                 break
             for e in self.engines:
-                e.step(x)
-            for e in self.engines:
-                e.sync()
-            self._do_exchange(x, self.kinds[x % 24])
+                e.enqueue_hour(x)
+            self._do_exchange(x, exchange_kind(self.plan, self.kinds, x))
             for i, e in enumerate(self.engines):
                 rows[i, x - first_hour] = e.finish_hour(x)
             hour = x + 1

@@ -126,6 +126,9 @@ int epi_reset(epi_engine* e);
  * Citizen::perform_operation for every agent against the start-of-hour map, lowest-agent-id conflict
  * resolution, swap, and Counts::update_counts.  out->hour = hour. */
 int epi_step(epi_engine* e, uint32_t hour, epi_counts* out);
+/* epi_step without waiting for the hour to finish and without its Counts row: the multi-region loop enqueues the exchange hour,
+ * packs the leavers behind it on the same stream and reads the row from epi_finish_hour. */
+int epi_enqueue_hour(epi_engine* e, uint32_t hour);
 /* Same hour with every random draw injected: draws[agent * EPI_DRAWS_PER_AGENT + slot] (host memory).
  * This is the bit-exact sub-step test entry (no reference equivalent; the reference cannot inject draws). */
 int epi_step_with_draws(epi_engine* e, uint32_t hour, const uint64_t* draws, epi_counts* out);
@@ -162,10 +165,14 @@ int epi_intervention_events(const epi_engine* e, epi_intervention_event* out, ui
 /* Selects the leaving agents (Citizen::is_commuter / can_migrate + gen_bool(percent_outgoing), citizen/mod.rs:456-495),
  * allots migrators to regions (EngineMigrationPlan::alloc_outgoing_to_regions, engine_migration_plan.rs:51-77), writes
  * their records into the destination's segment of send_buf and removes them from the region.  counts_out[n_regions]
- * (HOST) = records per destination.  Every segment header is written, also when nobody travels. */
+ * (HOST) = records per destination.  Every segment header is written, also when nobody travels.
+ * counts_out == NULL defers: the call returns with the kernels in flight on the engine's stream (the collective can be
+ * queued behind them at once) and errors surface in the next epi_finish_hour. */
 int epi_travel_pack(epi_engine* e, uint32_t hour, int kind, void* send_buf, uint64_t stride_records, uint32_t* counts_out);
 /* Installs the arrivals of recv_buf in order of source region.  assimilate_migrators / assimilate_commuters
- * (allocation_map.rs:214-277).  counts_in[n_regions] (HOST, may be NULL) receives the records per source region. */
+ * (allocation_map.rs:214-277).  counts_in[n_regions] (HOST) receives the records per source region; counts_in == NULL
+ * defers like epi_travel_pack (epi_finish_hour settles, including further placement rounds if some arrival is still
+ * without a cell). */
 int epi_travel_unpack(epi_engine* e, uint32_t hour, int kind, const void* recv_buf, uint64_t stride_records, uint32_t* counts_in);
 /* The tail of the multi-engine hour (epidemiology_simulation.rs:492-503): Counts after the travel adjustments,
  * process_interventions, and stop_simulation's MultiEngine arm (:564-571, records lockdown.zero_infection_hour). */

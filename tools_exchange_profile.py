@@ -29,9 +29,11 @@ with torch.cuda.stream(stream):
     for day in range(days):
         for h in range(24):
             x = hour + h
-            if x % 24 in m.kinds:
-                kind = m.kinds[x % 24]; tag = 'mig' if kind == 0 else 'com'
-                timed('step', lambda: eng.step(x))
+            from epirust_b200.multi import exchange_kind
+            kind = exchange_kind(plan, m.kinds, x)
+            if kind is not None:
+                tag = 'mig' if kind == 0 else 'com'
+                timed('step', lambda: eng.enqueue_hour(x))
                 counts = timed('pack_' + tag, lambda: eng.travel_pack(x, kind, m.send[0].data_ptr(), m.stride))
                 recv = timed('nccl_' + tag, lambda: m.exchange.exchange(m.send[0]))
                 timed('unpack_' + tag, lambda: eng.travel_unpack(x, kind, recv.data_ptr(), m.stride))
