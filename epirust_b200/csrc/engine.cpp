@@ -689,23 +689,30 @@ int epi_set_state(epi_engine* e, uint32_t n, const int32_t* cx, const int32_t* c
     if (n != e->P.n) return engine_fail(e, EPI_ERR_ARG, "epi_set_state: n must equal epi_capacity()");
     if (e->multi) return engine_fail(e, EPI_ERR_STATE, "epi_set_state is not available on a multi-region engine");
     CU(cudaSetDevice(e->device));
-    HostAgents a;
-    a.resize(n);
-    for (uint32_t i = 0; i < n; ++i) {
-        a.reg[i] = (uint32_t)e->P.region | ((uint32_t)e->P.region << 8);
-        if (cx[i] < 0 || cy[i] < 0 || (uint32_t)cx[i] >= e->geo.pitch || (uint32_t)cy[i] >= e->geo.rows)
-            return engine_fail(e, EPI_ERR_ARG, "epi_set_state: cell outside the grid");
-        const uint32_t ws = (st[i] >> ST_WS_SHIFT) & 3u;
-        if (home[i] >= e->geo.n_houses || (ws != WS_NA && work[i] >= e->geo.n_offices))
-            return engine_fail(e, EPI_ERR_ARG, "epi_set_state: house/office index out of range");
-        a.cell[i] = ((uint32_t)cy[i] << CELL_BITS) | (uint32_t)cx[i];
-        a.st[i] = st[i]; a.t0[i] = t0[i];
-        a.home[i] = house_origin(e->geo, home[i]);
-        a.work[i] = ws == WS_NA ? 0u : office_origin(e->geo, work[i]);
-        a.wsa[i] = wsa[i];
+    // The caller's arrays go to the device as they are (no host-side pass over the population); a kernel packs the cells and
+    // turns the house / office indices into origins.  cell_x / cell_y are staged in the claim array, which is zeroed again
+    // before its next use (claim_dirty).
+    const size_t nb = (size_t)n * sizeof(uint32_t);
+    if (grid_alloc_bytes(e) * sizeof(uint32_t) < 2 * nb) return engine_fail(e, EPI_ERR_STATE, "epi_set_state: grid too small to stage the cell arrays");
+    int32_t* d_cx = (int32_t*)e->D.claim;
+    int32_t* d_cy = d_cx + n;
+    e->claim_dirty = true;
+    CU(cudaMemcpyAsync(d_cx, cx, nb, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemcpyAsync(d_cy, cy, nb, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemcpyAsync(e->D.st, st, nb, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemcpyAsync(e->D.t0, t0, nb, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemcpyAsync(e->D.home, home, nb, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemcpyAsync(e->D.work, work, nb, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemcpyAsync(e->D.wsa, wsa, nb, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemsetAsync(e->d_misc + 2, 0, sizeof(uint32_t), e->stream));
+    {
+        Timed t(e, KK_MISC);
+        launch_import_state(e->P, e->D, d_cx, d_cy, e->geo.n_houses, e->geo.n_offices, e->d_misc + 2, e->stream);
     }
-    int rc = upload_agents(e, a);
-    if (rc) return rc;
+    uint32_t bad = 0;
+    CU(cudaMemcpyAsync(&bad, e->d_misc + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    if (bad) return engine_fail(e, EPI_ERR_ARG, "epi_set_state: " + std::to_string(bad) + " agents with a cell outside the grid or a house / office index out of range");
     return rebuild_grid(e);
 }
 

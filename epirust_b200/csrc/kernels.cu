@@ -508,8 +508,32 @@ __global__ void __launch_bounds__(256) k_build_grid(Params P, const uint32_t* __
     if ((old >> shift) & 0xFFu) atomicAdd(collisions, 1u);
 }
 
+// epi_set_state: the caller's arrays were copied to the device as they are (cell_x / cell_y into scratch, house / office INDICES
+// into home[] / work[]); pack the cell, turn the indices into origins, validate.  bad[0] counts out-of-range entries.
+__global__ void __launch_bounds__(256) k_import_state(Params P, DevPtrs D, const int32_t* __restrict__ cx, const int32_t* __restrict__ cy, uint32_t n_houses,
+                                                       uint32_t n_offices, uint32_t* __restrict__ bad) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n) return;
+    const uint32_t s = D.st[i];
+    const uint32_t ws = (s >> ST_WS_SHIFT) & 3u;
+    const int x = cx[i], y = cy[i];
+    const uint32_t h = D.home[i], w = D.work[i];
+    if (x < 0 || y < 0 || (uint32_t)x >= P.pitch || (uint32_t)y >= P.rows || h >= n_houses || (ws != WS_NA && w >= n_offices)) {
+        atomicAdd(bad, 1u);
+        return;
+    }
+    D.cell[i] = ((uint32_t)y << CELL_BITS) | (uint32_t)x;
+    D.home[i] = ((uint32_t)(P.housing().sy + 2 * (int)(h / (uint32_t)P.house_nx)) << CELL_BITS) | (uint32_t)(P.housing().sx + 2 * (int)(h % (uint32_t)P.house_nx));
+    D.work[i] = ws == WS_NA ? 0u : ((uint32_t)(P.work.sy + 10 * (int)(w / (uint32_t)P.office_nx)) << CELL_BITS) | (uint32_t)(P.work.sx + 10 * (int)(w % (uint32_t)P.office_nx));
+    D.reg[i] = (uint32_t)P.region | ((uint32_t)P.region << 8);
+    D.prop[i] = 0;
+}
+
 // ---- launchers ---------------------------------------------------------------------------------------------------
 static inline unsigned blocks_for(uint32_t n) { return (n + 255u) / 256u; }
+void launch_import_state(const Params& P, const DevPtrs& D, const int32_t* cx, const int32_t* cy, uint32_t n_houses, uint32_t n_offices, uint32_t* bad, cudaStream_t s) {
+    k_import_state<<<blocks_for(P.n), 256, 0, s>>>(P, D, cx, cy, n_houses, n_offices, bad);
+}
 
 void launch_hospital_scan(const Params& P, const DevPtrs& D, cudaStream_t s) {
     const Rect h = P.hospital();

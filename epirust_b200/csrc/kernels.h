@@ -14,6 +14,7 @@ void launch_sleep(const Params& P, const DevPtrs& D, uint32_t hour_offset, cudaS
 void launch_lock(const Params& P, const DevPtrs& D, cudaStream_t s);
 void launch_unlock(const Params& P, const DevPtrs& D, cudaStream_t s);
 void launch_vaccinate(const Params& P, const DevPtrs& D, uint64_t thr, uint32_t hour, cudaStream_t s);
+void launch_import_state(const Params& P, const DevPtrs& D, const int32_t* cx, const int32_t* cy, uint32_t n_houses, uint32_t n_offices, uint32_t* bad, cudaStream_t s);
 void launch_build_grid(const Params& P, const DevPtrs& D, uint32_t* collisions, cudaStream_t s);
 // travel.cu (each returns the number of kernels it launched)
 unsigned launch_travel_leave(const Params& P, const DevPtrs& D, const TravelArgs& A, const TravelPtrs& T, uint32_t* block_counts, TravelRecord* send,
