@@ -85,6 +85,16 @@ class ClockSampler:
                 "samples": len(sm), "reasons": reasons}
 
 
+def measured_traffic(workload):
+    """DRAM bytes of one active-hour pass (k_hour + k_commit) from the committed ncu --set full capture, or None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        t = json.load(open(p))
+        return float(t["pass_dram_bytes_per_launch"]) if t.get("workload") == workload else None
+    except Exception:
+        return None
+
+
 def algorithmic_bytes(n_agents, first_hour, n_hours):
     total = 0.0
     for h in range(first_hour, first_hour + n_hours):
@@ -240,7 +250,7 @@ def run_ours(args):
     achieved = ACTIVE_BYTES * n / (pass_ms * 1e-3) / 1e9
     day_bytes = algorithmic_bytes(n, 24 * W + 1, 24 * K)
     roofline = {
-        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": measured_traffic(args.workload) if not multi else None,
         "kernel": "active-hour pass = k_hour (propose + transitions + counts + claim) + k_commit (lowest-id claim resolution)",
         "algorithmic_bytes_per_launch": ACTIVE_BYTES * n, "avg_launch_ms": pass_ms, "peak_source": peak_src,
         "per_kernel_ms": {"k_hour": hour_ms, "k_commit": commit_ms, "k_sleep": sleep_ms, "k_hospital_scan": kt["hospital_scan"][0] / max(1, kt["hospital_scan"][1]),

@@ -7,7 +7,7 @@ timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1
 timeout 300 python __graft_entry__.py --smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/smoke.log
 timeout 600 python bench.py --steps 20 --warmup 3 > gpurun_out/bench_10m.json 2> gpurun_out/bench_10m.err
 timeout 300 python bench.py --workload 1m --steps 40 --warmup 3 --no-cpu-baseline > gpurun_out/bench_1m.json 2> gpurun_out/bench_1m.err
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_hour -s 40 -c 2 -o gpurun_out/prof_hour python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_hour.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_commit -s 40 -c 2 -o gpurun_out/prof_commit python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_commit.log 2>&1
 tail -3 gpurun_out/pytest_gpu.log; tail -2 gpurun_out/smoke.log; cat gpurun_out/bench_10m.json; tail -3 gpurun_out/bench_10m.err; cat gpurun_out/bench_1m.json

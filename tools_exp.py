@@ -7,9 +7,10 @@ from epirust_b200 import build as B
 B.build()
 os.makedirs(os.path.join(ROOT, "exp"), exist_ok=True)
 objs = [os.path.join(B.PKG, "build", s + ".o") for s in B.LIB_SOURCES if s != "kernels.cu"]
-for n in sys.argv[1:]:
-    o = os.path.join(ROOT, "exp", f"kernels_{n}.o")
-    subprocess.check_call([B._nvcc()] + B.NVCC_FLAGS + ["-I", os.path.join(ROOT, "include"), f"-DEPI_EXP={n}", "-Xptxas", "-v", "-c", os.path.join(B.CSRC, "kernels.cu"), "-o", o],
-                          stderr=open(os.path.join(ROOT, "exp", f"ptxas_{n}.log"), "w"))
-    subprocess.check_call([B._nvcc(), "-shared", "-ccbin", "/usr/bin/g++", "-Xcompiler", "-fopenmp", "-o", os.path.join(ROOT, "exp", f"lib_{n}.so"), o] + objs)
+for n in sys.argv[1:]:  # "3" or "3:8" = EPI_EXP 3 with EPI_PF 8
+    o = os.path.join(ROOT, "exp", f"kernels_{n.replace(':', '_')}.o")
+    exp, _, pf = n.partition(":")
+    subprocess.check_call([B._nvcc()] + B.NVCC_FLAGS + ["-I", os.path.join(ROOT, "include"), f"-DEPI_EXP={exp}"] + ([f"-DEPI_PF={pf}"] if pf else []) + [ "-Xptxas", "-v", "-c", os.path.join(B.CSRC, "kernels.cu"), "-o", o],
+                          stderr=open(os.path.join(ROOT, "exp", f"ptxas_{n.replace(':', '_')}.log"), "w"))
+    subprocess.check_call([B._nvcc(), "-shared", "-ccbin", "/usr/bin/g++", "-Xcompiler", "-fopenmp", "-o", os.path.join(ROOT, "exp", f"lib_{n.replace(':', '_')}.so"), o] + objs)
     print("built", n)
