@@ -685,6 +685,30 @@ int epi_get_state(epi_engine* e, int32_t* cx, int32_t* cy, uint32_t* st, uint32_
     return EPI_OK;
 }
 
+int epi_build_population(const epi_config* cfg, uint64_t seed, int32_t* cx, int32_t* cy, uint32_t* st, uint32_t* t0, uint32_t* home, uint32_t* work,
+                         uint32_t* wsa) {
+    if (!cfg || !cx || !cy || !st || !t0 || !home || !work || !wsa) return EPI_ERR_ARG;
+    try {
+        if (!validate_config(*cfg).empty()) return EPI_ERR_CONFIG;
+        const Geometry geo = make_geometry(cfg->grid_size, cfg->number_of_agents, cfg->hospital_beds_percentage);
+        HostAgents a;
+        build_population(*cfg, geo, seed, 0, a);
+        for (size_t i = 0; i < a.size(); ++i) {
+            const uint32_t ws = (a.st[i] >> ST_WS_SHIFT) & 3u;
+            cx[i] = (int32_t)(a.cell[i] & CELL_XMASK);
+            cy[i] = (int32_t)(a.cell[i] >> CELL_BITS);
+            st[i] = a.st[i];
+            t0[i] = 0;
+            home[i] = house_index_of(geo, a.home[i]);
+            work[i] = ws == WS_NA ? 0u : office_index_of(geo, a.work[i]);
+            wsa[i] = ws == WS_STAFF ? a.wsa[i] : 0u;
+        }
+    } catch (const std::exception&) {
+        return EPI_ERR_CONFIG;
+    }
+    return EPI_OK;
+}
+
 int epi_set_state(epi_engine* e, uint32_t n, const int32_t* cx, const int32_t* cy, const uint32_t* st, const uint32_t* t0, const uint32_t* home,
                   const uint32_t* work, const uint32_t* wsa) {
     if (!e || !cx || !cy || !st || !t0 || !home || !work || !wsa) return engine_fail(e, EPI_ERR_ARG, "null argument");

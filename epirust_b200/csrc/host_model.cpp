@@ -2,6 +2,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <stdexcept>
 #include <unordered_set>
 
@@ -17,6 +18,37 @@ constexpr uint32_t kRoutineWorkTime = 8;            // models/constants.rs:32
 
 inline int ceil_frac(uint32_t g, double f) { return (int)std::ceil((double)g * f); }
 }  // namespace
+
+// Agent numbering.  The reference hands houses and offices out round-robin in creation order (houses[i % H],
+// offices[i % O], grid.rs:108-113), so the agent created as number c shares house c % H with c+H, c+2H, ...; agent
+// identities themselves are arbitrary (Uuid v4).  We number the same population HOUSE BY HOUSE: agent id i is the
+// rank-th occupant of house `house`, and stands for the reference's creation number c = house + rank * H (so the
+// pairing of houses with offices is the reference's).  Housemates then sit in adjacent slots of every per-agent array:
+// the claim words and grid bytes of a house are touched by neighbouring threads of one kernel instead of threads
+// millions of agents apart (each 32-byte claim sector makes one trip to DRAM per kernel instead of two at the home
+// hours).  EPI_AGENT_ORDER=creation keeps id == creation number (the A/B switch the measurement in DESIGN.md used).
+bool house_major_order() {
+    static const bool v = [] {
+        const char* e = getenv("EPI_AGENT_ORDER");
+        return !(e && std::string(e) == "creation");
+    }();
+    return v;
+}
+HouseSlot house_slot(uint32_t i, uint32_t n, uint32_t H) {
+    HouseSlot s;
+    if (!house_major_order()) {
+        s.house = i % H;
+        s.rank = i / H;
+        s.housemates = (n - 1 - s.house) / H + 1;  // agents house, house+H, ... < n
+    } else {
+        const uint32_t q = n / H, r = n % H;  // houses 0..r-1 hold q+1 agents, the others q
+        const uint64_t big = (uint64_t)r * (q + 1);
+        if (i < big) { s.house = i / (q + 1); s.rank = i % (q + 1); s.housemates = q + 1; }
+        else { const uint32_t j = (uint32_t)(i - big); s.house = r + j / q; s.rank = j % q; s.housemates = q; }
+    }
+    s.creation = s.house + s.rank * H;
+    return s;
+}
 
 Geometry make_geometry(uint32_t grid_size, uint32_t n_agents, double beds_pct) {
     // Vertical strips, 40 % housing / 20 % transport / 20 % work / 10 % hospital of the width, each G+1 rows tall
@@ -163,8 +195,9 @@ void build_population(const epi_config& c, const Geometry& g, uint64_t seed, int
         const uint32_t immunity_plus2 = (uint32_t)mulhi64(draw(i, IS_IMMUNITY), 5);
         out.st[i] = ST_S | (immunity_plus2 << ST_IMM_SHIFT) | (pt ? ST_PT : 0u) | (ws << ST_WS_SHIFT) | (AK_HOME << ST_AREA_SHIFT);
         out.t0[i] = 0;
-        out.home[i] = house_origin(g, i % g.n_houses);
-        out.work[i] = working ? office_origin(g, i % g.n_offices) : 0u;
+        const HouseSlot hs = house_slot(i, n, g.n_houses);
+        out.home[i] = house_origin(g, hs.house);
+        out.work[i] = working ? office_origin(g, hs.creation % g.n_offices) : 0u;
         out.wsa[i] = ws == WS_STAFF ? kRoutineWorkTime : 0u;
         out.reg[i] = (uint32_t)region | ((uint32_t)region << 8);
     }
@@ -190,13 +223,12 @@ void build_population(const epi_config& c, const Geometry& g, uint64_t seed, int
     infect(c.infected_mild_symptomatic, ST_I, SEV_MILD, 1);
     infect(c.infected_severe, ST_I, SEV_SEVERE, 1);
 
-    // start cells: agent i lives in house i % H together with i+H, i+2H, ...; the k housemates take the first k of
-    // (sx,sy),(sx,sy+1),(sx+1,sy),(sx+1,sy+1); a lone occupant gets a uniformly random corner (area.rs:64-74)
+    // start cells: the k housemates of a house take the first k of (sx,sy),(sx,sy+1),(sx+1,sy),(sx+1,sy+1) in creation
+    // order; a lone occupant gets a uniformly random corner (area.rs:64-74)
     const uint32_t H = g.n_houses;
     for (uint32_t i = 0; i < n; ++i) {
-        const uint32_t house = i % H;
-        const uint32_t housemates = (n - 1 - house) / H + 1;  // agents house, house+H, ... < n
-        const uint32_t rank = i / H;
+        const HouseSlot hs = house_slot(i, n, H);
+        const uint32_t house = hs.house, housemates = hs.housemates, rank = hs.rank;
         const int sx = g.housing.sx + 2 * (int)(house % (uint32_t)g.house_nx);
         const int sy = g.housing.sy + 2 * (int)(house / (uint32_t)g.house_nx);
         int x, y;

@@ -38,6 +38,14 @@ inline uint32_t office_index_of(const Geometry& g, uint32_t origin) {
     return (uint32_t)((y - g.work.sy) / 10 * g.office_nx + (x - g.work.sx) / 10);
 }
 
+// which house agent id i lives in (see the "Agent numbering" note in host_model.cpp)
+struct HouseSlot {
+    uint32_t house, rank, housemates;  // house index, position among its occupants, number of occupants
+    uint32_t creation;                 // the reference's creation number of this agent: house + rank * n_houses
+};
+bool house_major_order();
+HouseSlot house_slot(uint32_t agent, uint32_t n_agents, uint32_t n_houses);
+
 struct HostAgents {
     std::vector<uint32_t> cell, st, t0, home, work, wsa, reg;
     size_t size() const { return st.size(); }

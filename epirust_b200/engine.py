@@ -266,6 +266,16 @@ class Engine:
         return int(self.L.epi_device_bytes(self.h))
 
 
+def build_population(cfg, seed=1):
+    """The Auto population factory on the host (epi_build_population; no GPU needed): dict of arrays like Engine.get_state()."""
+    L = _ffi.load()
+    arrs = {f: np.zeros(cfg.number_of_agents, dt) for f, dt in zip(STATE_FIELDS, STATE_DTYPES)}
+    rc = L.epi_build_population(C.byref(cfg), seed, *[_ptr(arrs[f]) for f in STATE_FIELDS])
+    if rc != 0:
+        raise EpiError(f"epi_build_population failed with status {rc}")
+    return arrs
+
+
 def run_standalone(cfg, seed=1, device=0, output_dir=None, engine_id="0"):
     """EngineApp::start_standalone: whole run with interventions; returns (rows[n,7], hour-loop seconds)."""
     L = _ffi.load()

@@ -197,6 +197,12 @@ int epi_get_state(epi_engine* e, int32_t* cell_x, int32_t* cell_y, uint32_t* st,
                   uint32_t* wsa);
 int epi_set_state(epi_engine* e, uint32_t n, const int32_t* cell_x, const int32_t* cell_y, const uint32_t* st, const uint32_t* t0,
                   const uint32_t* home, const uint32_t* work, const uint32_t* wsa);
+/* Host only (no GPU needed): the Auto population factory -- Grid::generate_population + citizen_factory +
+ * set_starting_infections + the essential-worker draw of init_interventions (engine/src/geography/grid.rs:83-155,
+ * citizen/citizen_factory.rs:31-134, epidemiology_simulation.rs:178-192) -- as the arrays epi_create uploads, in the
+ * layout of epi_get_state.  Arrays of cfg->number_of_agents entries. */
+int epi_build_population(const epi_config* cfg, uint64_t seed, int32_t* cell_x, int32_t* cell_y, uint32_t* st, uint32_t* t0,
+                         uint32_t* home, uint32_t* work, uint32_t* wsa);
 /* out[0..3] housing sx,sy,ex,ey; [4..7] transport; [8..11] work; [12..15] hospital (current); [16] houses; [17] offices;
  * [18] grid_size.  (geography/mod.rs:33-70, grid.rs:240-261) */
 int epi_geometry(const epi_engine* e, int32_t* out19);

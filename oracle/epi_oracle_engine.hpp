@@ -7,6 +7,8 @@
 #pragma once
 #include <omp.h>
 
+#include <cstdlib>
+
 #include <map>
 #include <unordered_set>
 
@@ -214,11 +216,28 @@ struct Engine {
         agents.resize(n);
         size_t pt_users = 0;
         const size_t H = grid.houses.size(), O = grid.offices.size();
+        // Agent numbering (a convention shared with the engine under test, not reference behaviour): the reference gives
+        // the agent it creates as number c the house c % H and the office c % O (grid.rs:108-113); ids are opaque Uuids.
+        // Agent id i here is the rank-th occupant of house house_of[i], i.e. the reference's creation number
+        // c = house + rank * H -- the same population, numbered house by house.  EPI_AGENT_ORDER=creation: id == c.
+        const char* order_env = getenv("EPI_AGENT_ORDER");
+        const bool by_house = !(order_env && std::string(order_env) == "creation");
+        std::vector<uint32_t> house_of(n), rank_of(n);
+        {
+            uint32_t i = 0;
+            if (by_house) {
+                for (uint32_t h = 0; h < H && i < n; ++h)
+                    for (uint32_t c = h, k = 0; c < n; c += (uint32_t)H, ++k) { house_of[i] = h; rank_of[i] = k; ++i; }
+            } else {
+                for (; i < n; ++i) { house_of[i] = i % (uint32_t)H; rank_of[i] = i / (uint32_t)H; }
+            }
+        }
         for (uint32_t i = 0; i < n; ++i) {  // create_citizen citizen_factory.rs:58-88
             Rng r = engine_rng(i, 0, DOM_INIT);
             bool is_working = r.gen_bool(IS_WORKING, cfg.working_percentage);
-            Area home = grid.houses[i % H];
-            Area work = grid.offices[i % O];
+            const uint32_t creation = house_of[i] + rank_of[i] * (uint32_t)H;
+            Area home = grid.houses[house_of[i]];
+            Area work = grid.offices[creation % O];
             bool uses_pt = r.gen_bool(IS_PT, cfg.public_transport_percentage) && is_working && pt_users < n_transport_locations;
             if (uses_pt) pt_users++;
             Citizen z;
@@ -254,15 +273,14 @@ struct Engine {
         // k>=2 -> both xs and both ys are chosen (order preserved), x outer / y inner, take k; k==1 -> one random x, one random y.
         std::vector<uint8_t> per_house(H, 0);
         for (uint32_t i = 0; i < n; ++i) {
-            if (per_house[i % H] >= constants::HOME_SIZE * constants::HOME_SIZE)
+            if (per_house[house_of[i]] >= constants::HOME_SIZE * constants::HOME_SIZE)
                 throw std::runtime_error("There are more agents assigned to a house than house capacity");  // grid.rs:140-142
-            per_house[i % H]++;
+            per_house[house_of[i]]++;
         }
         home_loc.resize(n);
-        std::vector<uint8_t> rank(H, 0);
         for (uint32_t i = 0; i < n; ++i) {
             const Area& home = agents[i].home_location;
-            uint32_t k = per_house[i % H], j = rank[i % H]++;
+            uint32_t k = per_house[house_of[i]], j = rank_of[i];
             if (k == 1) {
                 Rng r = engine_rng(i, 0, DOM_INIT);
                 int x = home.start_offset.x + (int)r.choose_index(IS_STARTX, 2);
