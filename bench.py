@@ -16,7 +16,6 @@ built in this image (no cargo/rustc), so kind = "port".
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -51,38 +50,65 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks and throttle reasons during the timed region."""
-    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock, power and throttle reasons of the benched GPU DURING the timed region: NVML polled from a thread every
+    ~2 ms (the timed region of a default run is a fraction of a second, too short for `nvidia-smi -lms`)."""
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
     def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+        self.index, self.rows, self.t, self.h, self.nv, self.err = index, [], None, None, None, None
+        self.stop_flag = threading.Event()
+        try:
+            import pynvml as nv
+            import torch
+
+            nv.nvmlInit()
+            try:  # CUDA_VISIBLE_DEVICES may renumber: find the device by UUID
+                self.h = nv.nvmlDeviceGetHandleByUUID(("GPU-" + str(torch.cuda.get_device_properties(index).uuid)).encode())
+            except Exception:
+                self.h = nv.nvmlDeviceGetHandleByIndex(index)
+            self.nv = nv
+            self.sm_max = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+        except Exception as ex:  # noqa: BLE001
+            self.err = f"NVML unavailable: {ex}"
+
+    def _reasons(self):
+        nv = self.nv
+        for name in ("nvmlDeviceGetCurrentClocksEventReasons", "nvmlDeviceGetCurrentClocksThrottleReasons"):
+            f = getattr(nv, name, None)
+            if f is not None:
+                try:
+                    return int(f(self.h))
+                except Exception:  # noqa: BLE001
+                    continue
+        return 0
+
+    def _poll(self):
+        nv = self.nv
+        while not self.stop_flag.is_set():
+            try:
+                self.rows.append((float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)), nv.nvmlDeviceGetPowerUsage(self.h) / 1e3, self._reasons()))
+            except Exception as ex:  # noqa: BLE001
+                self.err = str(ex)
+                return
+            time.sleep(0.002)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+        if self.nv is None:
+            return
+        self.t = threading.Thread(target=self._poll, daemon=True)
+        self.t.start()
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
-        self.proc.terminate()
+        if self.t is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "power_w_max": None, "samples": 0, "reasons": [self.err or "not sampled"]}
+        self.stop_flag.set()
         self.t.join(timeout=2)
-        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        pw = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for k, n in enumerate(names) if any(len(r) > 3 + k and r[3 + k].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None, "power_w_max": max(pw) if pw else None,
-                "samples": len(sm), "reasons": reasons}
+        sm = sorted(r[0] for r in self.rows)
+        mask = 0
+        for r in self.rows:
+            mask |= r[2]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.sm_max, "power_w_max": max((r[1] for r in self.rows), default=None),
+                "samples": len(sm), "reasons": [n for bit, n in self.REASONS if mask & bit]}
 
 
 def measured_traffic(workload):

@@ -39,6 +39,9 @@
 
 namespace epi {
 
+#ifndef EPI_MINB
+#define EPI_MINB 6  // resident CTAs per SM the movement-hour kernel is compiled for (40 registers; 8 -> 32 registers + spills, measured slower)
+#endif
 enum : int { MODE_STAY = 0, MODE_WALK = 1, MODE_GOTO = 2 };
 enum : int { KIND_START = 0, KIND_MOVE = 1, KIND_END = 2 };
 
@@ -59,7 +62,7 @@ __device__ __forceinline__ uint32_t ld_early_rw(const uint32_t* p) {  // for arr
 // agents): the first of the two dependent memory round trips of an agent-hour then costs an L2 hit instead of a DRAM access
 // (+5 % agent-steps/s at 10 M agents; half a wave is as good, 2 and 4 waves are worse; prefetching the grid rows of the agent
 // ahead as well costs more issue slots than it saves).
-constexpr uint32_t PREFETCH_AHEAD = 148u * 6u * 256u;
+constexpr uint32_t PREFETCH_AHEAD = 148u * 6u * 256u;  // one wave at 6 CTAs / SM
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void st_stream(uint32_t* p, uint32_t v) { asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
@@ -227,8 +230,12 @@ __global__ void __launch_bounds__(256) k_hospital_scan(Params P, const uint8_t* 
     }
 }
 
-template <int KIND, bool INJECT>
-__global__ void __launch_bounds__(256, KIND == KIND_MOVE ? 6 : 4) k_hour(Params P, DevPtrs D, uint32_t hour_offset, uint32_t h) {
+// PLAIN: an hour of day at which perform_movements has no special case for anybody but hospital staff (h = 9..11, 13..15,
+// 18..22: everybody who can move walks inside current_area) -- 11 of the 16 movement hours.  The kernel is issue-bound,
+// so the goto / area-change logic is compiled out for them (h is then a dummy).
+template <int KIND, bool INJECT, bool PLAIN = false>
+__global__ void __launch_bounds__(256, KIND == KIND_MOVE ? EPI_MINB : 4) k_hour(Params P, DevPtrs D, uint32_t hour_offset, uint32_t h_arg) {
+    const uint32_t h = PLAIN ? 9u : h_arg;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n) return;
     if ((threadIdx.x & 7u) == 0 && i + PREFETCH_AHEAD < P.n) {  // one prefetch per 32-byte sector
@@ -559,11 +566,20 @@ void launch_hospital_scan(const Params& P, const DevPtrs& D, cudaStream_t s) {
     if (blocks == 0) blocks = 1;
     k_hospital_scan<<<blocks, 256, 0, s>>>(P, D.grid, D.hosp_first);
 }
+// citizen/mod.rs:257-349: the hours of day perform_movements treats specially are 7, 8, 12, 16, 17
+static inline bool hour_is_plain(uint32_t h) {
+#if defined(EPI_EXP) && (EPI_EXP & 1)
+    return false;
+#else
+    return h >= 9 && h <= 22 && h != 12 && h != 16 && h != 17;
+#endif
+}
 template <bool INJECT>
 static void launch_hour_t(const Params& P, const DevPtrs& D, uint32_t hour_of_day, uint32_t hour_offset, cudaStream_t s) {
     const unsigned b = blocks_for(P.n);
     if (hour_of_day == 0) k_hour<KIND_START, INJECT><<<b, 256, 0, s>>>(P, D, hour_offset, hour_of_day);
     else if (hour_of_day == 23) k_hour<KIND_END, INJECT><<<b, 256, 0, s>>>(P, D, hour_offset, hour_of_day);
+    else if (hour_is_plain(hour_of_day)) k_hour<KIND_MOVE, INJECT, true><<<b, 256, 0, s>>>(P, D, hour_offset, hour_of_day);
     else k_hour<KIND_MOVE, INJECT><<<b, 256, 0, s>>>(P, D, hour_offset, hour_of_day);
 }
 void launch_hour(const Params& P, const DevPtrs& D, uint32_t hour_of_day, uint32_t hour_offset, bool inject, cudaStream_t s) {
