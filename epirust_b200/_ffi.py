@@ -48,6 +48,7 @@ class EpiConfig(C.Structure):
         ("n_vaccinations", C.c_int32),
         ("vaccinate_at_hour", C.c_uint32 * 8),
         ("vaccinate_percent", C.c_double * 8),
+        ("population_csv_file", C.c_char * 256),  # Population::Csv.file, b"" for Population::Auto
     ]
 
 
@@ -71,7 +72,7 @@ EXPORTS = [
     "epi_create", "epi_create_region", "epi_create_multi", "epi_destroy", "epi_last_error", "epi_population", "epi_capacity", "epi_counts_at_start",
     "epi_set_stream", "epi_travel_pack", "epi_travel_unpack", "epi_finish_hour", "epi_get_regions",
     "epi_sync", "epi_reset", "epi_step", "epi_enqueue_hour", "epi_step_with_draws", "epi_run_hours", "epi_simulate_hours", "epi_intervention_events", "epi_lock_city", "epi_unlock_city", "epi_vaccinate",
-    "epi_expand_hospital", "epi_get_state", "epi_set_state", "epi_build_population", "epi_geometry", "epi_get_grid", "epi_set_kernel_timing",
+    "epi_expand_hospital", "epi_get_state", "epi_set_state", "epi_build_population", "epi_population_size", "epi_geometry", "epi_get_grid", "epi_set_kernel_timing",
     "epi_get_kernel_times", "epi_launch_count", "epi_device_bytes", "epi_config_from_json", "epi_config_from_json_string",
     "epi_run_standalone", "epi_version",
 ]
@@ -122,6 +123,7 @@ def load():
     L.epi_get_state.argtypes = [vp] + [vp] * 7
     L.epi_set_state.argtypes = [vp, u32] + [vp] * 7
     L.epi_build_population.argtypes = [C.POINTER(EpiConfig), u64] + [vp] * 7
+    L.epi_population_size.argtypes = [C.POINTER(EpiConfig), C.POINTER(u32)]
     L.epi_geometry.argtypes = [vp, vp]
     L.epi_get_grid.argtypes = [vp, vp, u64, C.POINTER(u32), C.POINTER(u32)]
     L.epi_set_kernel_timing.argtypes = [vp, i32]

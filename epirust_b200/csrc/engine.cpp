@@ -382,9 +382,19 @@ int epi_create_region(const epi_config* cfg, uint64_t seed, int device, int regi
     return epi_create_multi(cfg, seed, device, region, nullptr, 0, out);
 }
 
-int epi_create_multi(const epi_config* cfg, uint64_t seed, int device, int region, const epi_travel_plan* plan, uint32_t extra_capacity, epi_engine** out) {
-    if (!cfg || !out) return engine_fail(nullptr, EPI_ERR_ARG, "null argument");
+int epi_create_multi(const epi_config* cfg_in, uint64_t seed, int device, int region, const epi_travel_plan* plan, uint32_t extra_capacity, epi_engine** out) {
+    if (!cfg_in || !out) return engine_fail(nullptr, EPI_ERR_ARG, "null argument");
     *out = nullptr;
+    // Population::Csv: the population file decides the number of agents (Grid::read_population, grid.rs:194-231)
+    PopulationRecords records;
+    epi_config resolved;
+    try {
+        resolved = resolve_population(*cfg_in, records);
+    } catch (const std::exception& ex) {
+        return engine_fail(nullptr, EPI_ERR_IO, ex.what());
+    }
+    const epi_config* cfg = &resolved;
+    const bool from_csv = resolved.population_csv_file[0] != 0;
     const std::string bad = validate_config(*cfg);
     if (!bad.empty()) return engine_fail(nullptr, EPI_ERR_CONFIG, bad);
     if (region < 0 || region > 254) return engine_fail(nullptr, EPI_ERR_ARG, "region must be in 0..254");
@@ -415,7 +425,7 @@ int epi_create_multi(const epi_config* cfg, uint64_t seed, int device, int regio
         e->geo = make_geometry(cfg->grid_size, cfg->number_of_agents, cfg->hospital_beds_percentage);
         e->P = make_params(*cfg, e->geo, seed, region);
         HostAgents agents;
-        build_population(*cfg, e->geo, seed, region, agents);
+        build_population(*cfg, e->geo, seed, region, agents, from_csv ? &records : nullptr);
         const uint32_t n_agents = cfg->number_of_agents, capacity = n_agents + extra_capacity;
         if (plan) {
             e->multi = true;
@@ -687,12 +697,15 @@ int epi_get_state(epi_engine* e, int32_t* cx, int32_t* cy, uint32_t* st, uint32_
 
 int epi_build_population(const epi_config* cfg, uint64_t seed, int32_t* cx, int32_t* cy, uint32_t* st, uint32_t* t0, uint32_t* home, uint32_t* work,
                          uint32_t* wsa) {
-    if (!cfg || !cx || !cy || !st || !t0 || !home || !work || !wsa) return EPI_ERR_ARG;
+    if (!cfg || !cx || !cy || !st || !t0 || !home || !work || !wsa) return engine_fail(nullptr, EPI_ERR_ARG, "null argument");
     try {
-        if (!validate_config(*cfg).empty()) return EPI_ERR_CONFIG;
-        const Geometry geo = make_geometry(cfg->grid_size, cfg->number_of_agents, cfg->hospital_beds_percentage);
+        PopulationRecords records;
+        const epi_config c = resolve_population(*cfg, records);
+        const std::string bad = validate_config(c);
+        if (!bad.empty()) return engine_fail(nullptr, EPI_ERR_CONFIG, bad);
+        const Geometry geo = make_geometry(c.grid_size, c.number_of_agents, c.hospital_beds_percentage);
         HostAgents a;
-        build_population(*cfg, geo, seed, 0, a);
+        build_population(c, geo, seed, 0, a, c.population_csv_file[0] ? &records : nullptr);
         for (size_t i = 0; i < a.size(); ++i) {
             const uint32_t ws = (a.st[i] >> ST_WS_SHIFT) & 3u;
             cx[i] = (int32_t)(a.cell[i] & CELL_XMASK);
@@ -703,8 +716,19 @@ int epi_build_population(const epi_config* cfg, uint64_t seed, int32_t* cx, int3
             work[i] = ws == WS_NA ? 0u : office_index_of(geo, a.work[i]);
             wsa[i] = ws == WS_STAFF ? a.wsa[i] : 0u;
         }
-    } catch (const std::exception&) {
-        return EPI_ERR_CONFIG;
+    } catch (const std::exception& ex) {
+        return engine_fail(nullptr, EPI_ERR_CONFIG, ex.what());
+    }
+    return EPI_OK;
+}
+
+int epi_population_size(const epi_config* cfg, uint32_t* n) {
+    if (!cfg || !n) return engine_fail(nullptr, EPI_ERR_ARG, "null argument");
+    try {
+        PopulationRecords records;
+        *n = resolve_population(*cfg, records).number_of_agents;
+    } catch (const std::exception& ex) {
+        return engine_fail(nullptr, EPI_ERR_IO, ex.what());
     }
     return EPI_OK;
 }

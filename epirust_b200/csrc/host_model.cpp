@@ -3,6 +3,8 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <fstream>
+#include <string>
 #include <stdexcept>
 #include <unordered_set>
 
@@ -19,35 +21,21 @@ constexpr uint32_t kRoutineWorkTime = 8;            // models/constants.rs:32
 inline int ceil_frac(uint32_t g, double f) { return (int)std::ceil((double)g * f); }
 }  // namespace
 
-// Agent numbering.  The reference hands houses and offices out round-robin in creation order (houses[i % H],
-// offices[i % O], grid.rs:108-113), so the agent created as number c shares house c % H with c+H, c+2H, ...; agent
-// identities themselves are arbitrary (Uuid v4).  We number the same population HOUSE BY HOUSE: agent id i is the
-// rank-th occupant of house `house`, and stands for the reference's creation number c = house + rank * H (so the
-// pairing of houses with offices is the reference's).  Housemates then sit in adjacent slots of every per-agent array:
-// the claim words and grid bytes of a house are touched by neighbouring threads of one kernel instead of threads
-// millions of agents apart (each 32-byte claim sector makes one trip to DRAM per kernel instead of two at the home
-// hours).  EPI_AGENT_ORDER=creation keeps id == creation number (the A/B switch the measurement in DESIGN.md used).
-bool house_major_order() {
-    static const bool v = [] {
+// Agent numbering.  The reference hands houses and offices out round-robin in creation order (houses[c % H], offices[c % O],
+// grid.rs:108-113), so the citizen created as number c shares house c % H with c+H, c+2H, ...; agent identities themselves
+// are arbitrary (Uuid v4).  We build exactly that population and then NUMBER it house by house: housemates sit in adjacent
+// slots of every per-agent array, so the claim words and grid bytes of a house are touched by neighbouring threads of one
+// kernel instead of threads millions of agents apart (each 32-byte claim sector makes one trip to DRAM per kernel instead
+// of two at the home hours: -5 % time per simulated day at 10 M agents).  EPI_AGENT_ORDER=creation keeps id == creation
+// number (the A/B switch behind that figure); the oracle follows the same variable.  Measured and rejected: numbering the
+// public-transport commuters last, so that the warps of the home hours are uniform -- the random accesses of the transport
+// strip then pile up at the end of every kernel instead of being spread over it (+3 % time).
+AgentOrder agent_order() {
+    static const AgentOrder v = [] {
         const char* e = getenv("EPI_AGENT_ORDER");
-        return !(e && std::string(e) == "creation");
+        return e && std::string(e) == "creation" ? AgentOrder::Creation : AgentOrder::House;
     }();
     return v;
-}
-HouseSlot house_slot(uint32_t i, uint32_t n, uint32_t H) {
-    HouseSlot s;
-    if (!house_major_order()) {
-        s.house = i % H;
-        s.rank = i / H;
-        s.housemates = (n - 1 - s.house) / H + 1;  // agents house, house+H, ... < n
-    } else {
-        const uint32_t q = n / H, r = n % H;  // houses 0..r-1 hold q+1 agents, the others q
-        const uint64_t big = (uint64_t)r * (q + 1);
-        if (i < big) { s.house = i / (q + 1); s.rank = i % (q + 1); s.housemates = q + 1; }
-        else { const uint32_t j = (uint32_t)(i - big); s.house = r + j / q; s.rank = j % q; s.housemates = q; }
-    }
-    s.creation = s.house + s.rank * H;
-    return s;
 }
 
 Geometry make_geometry(uint32_t grid_size, uint32_t n_agents, double beds_pct) {
@@ -92,7 +80,8 @@ Geometry make_geometry(uint32_t grid_size, uint32_t n_agents, double beds_pct) {
 
 std::string validate_config(const epi_config& c) {
     auto pct = [](double p) { return p >= 0.0 && p <= 1.0; };
-    if (c.number_of_agents == 0) return "population.Auto.number_of_agents must be > 0 (reference panics \"No citizens!\")";
+    if (c.number_of_agents == 0) return c.population_csv_file[0] ? "the population file holds no records (reference panics \"No citizens!\")"
+                                                                 : "population.Auto.number_of_agents must be > 0 (reference panics \"No citizens!\")";
     if (c.grid_size < 10) return "geography_parameters.grid_size must be >= 10 (no offices otherwise)";
     if (c.grid_size > MAX_COORD - 1) return "geography_parameters.grid_size must be <= 16382 (cell packing)";
     if (!pct(c.public_transport_percentage) || !pct(c.working_percentage) || !pct(c.hospital_beds_percentage)) return "percentage out of [0,1]";
@@ -162,17 +151,97 @@ Params make_params(const epi_config& c, const Geometry& g, uint64_t seed, int re
     return P;
 }
 
-void build_population(const epi_config& c, const Geometry& g, uint64_t seed, int region, HostAgents& out) {
+// ---- Population::Csv ---------------------------------------------------------------------------------------------------
+namespace {
+// one CSV record -> fields (RFC 4180 quoting, as the csv crate reads it by default)
+bool split_csv_line(const std::string& line, std::vector<std::string>& out) {
+    out.clear();
+    std::string cur;
+    bool quoted = false;
+    for (size_t i = 0; i < line.size(); ++i) {
+        const char ch = line[i];
+        if (quoted) {
+            if (ch == '"') {
+                if (i + 1 < line.size() && line[i + 1] == '"') { cur.push_back('"'); ++i; }
+                else quoted = false;
+            } else cur.push_back(ch);
+        } else if (ch == '"' && cur.empty()) quoted = true;
+        else if (ch == ',') { out.push_back(cur); cur.clear(); }
+        else cur.push_back(ch);
+    }
+    out.push_back(cur);
+    return !quoted;
+}
+}  // namespace
+
+PopulationRecords read_population_csv(const std::string& path) {
+    std::ifstream f(path);
+    if (!f) throw std::runtime_error("Could not read population file: " + path);  // grid.rs:202
+    PopulationRecords r;
+    std::string line;
+    std::vector<std::string> fields;
+    int col_ind = -1, col_age = -1, col_working = -1, col_pt = -1;
+    size_t n_cols = 0, line_no = 0;
+    auto fail = [&](const std::string& what) { throw std::runtime_error("Could not deserialize population line " + std::to_string(line_no) + ": " + what); };
+    auto parse_bool = [&](const std::string& v) -> uint8_t {  // population_record.rs:34-43
+        if (v == "True") return 1;
+        if (v == "False") return 0;
+        fail("invalid value: string \"" + v + "\", expected True or False");
+        return 0;
+    };
+    while (std::getline(f, line)) {
+        ++line_no;
+        if (!line.empty() && line.back() == '\r') line.pop_back();
+        if (line.empty()) continue;  // the csv crate skips empty lines
+        if (!split_csv_line(line, fields)) fail("unterminated quoted field");
+        if (n_cols == 0) {  // header row: serde maps the struct fields by column name, other columns are ignored
+            n_cols = fields.size();
+            for (size_t k = 0; k < fields.size(); ++k) {
+                if (fields[k] == "ind") col_ind = (int)k;
+                else if (fields[k] == "age") col_age = (int)k;
+                else if (fields[k] == "working") col_working = (int)k;
+                else if (fields[k] == "pub_transport") col_pt = (int)k;
+            }
+            if (col_ind < 0) fail("missing field `ind`");
+            if (col_age < 0) fail("missing field `age`");
+            if (col_working < 0) fail("missing field `working`");
+            if (col_pt < 0) fail("missing field `pub_transport`");
+            continue;
+        }
+        if (fields.size() != n_cols) fail("found record with " + std::to_string(fields.size()) + " fields, but the previous record has " + std::to_string(n_cols) + " fields");
+        const std::string& ind = fields[(size_t)col_ind];  // ind: u32
+        if (ind.empty() || ind.size() > 10 || ind.find_first_not_of("0123456789") != std::string::npos || std::stoull(ind) > 0xFFFFFFFFull) fail("invalid digit found in string (field `ind`)");
+        r.working.push_back(parse_bool(fields[(size_t)col_working]));
+        r.pub_transport.push_back(parse_bool(fields[(size_t)col_pt]));
+    }
+    return r;
+}
+
+epi_config resolve_population(const epi_config& cfg, PopulationRecords& records) {
+    epi_config c = cfg;
+    c.population_csv_file[EPI_PATH_MAX - 1] = 0;
+    if (c.population_csv_file[0]) {
+        records = read_population_csv(c.population_csv_file);
+        if (records.size() > (size_t)(1u << 27)) throw std::runtime_error("population file: more than 2^27 records");
+        c.number_of_agents = (uint32_t)records.size();
+    }
+    return c;
+}
+
+void build_population(const epi_config& c, const Geometry& g, uint64_t seed, int region, HostAgents& out, const PopulationRecords* records) {
     const uint32_t n = c.number_of_agents;
+    if (records && records->size() != n) throw std::runtime_error("population records do not match number_of_agents");
     if (g.n_houses == 0 || g.n_offices == 0) throw std::runtime_error("grid too small: no houses or offices");
     if ((uint64_t)n > 4ull * g.n_houses)
-        throw std::runtime_error("more than 4 agents per house: population does not fit the housing area (grid.rs:140-142)");
-    out.resize(n);
+        throw std::runtime_error(records ? "Cannot accommodate citizens into homes! There are " + std::to_string(n) + " citizens, but " + std::to_string(4ull * g.n_houses) + " home points"  // grid.rs:216-223
+                                         : std::string("more than 4 agents per house: population does not fit the housing area (grid.rs:140-142)"));
+    const uint32_t H = g.n_houses;
     const uint64_t thr_working = bernoulli_threshold(c.working_percentage);
     const uint64_t thr_pt = bernoulli_threshold(c.public_transport_percentage);
     const uint64_t thr_staff = bernoulli_threshold(kHospitalStaffPercentage);
     const uint64_t thr_essential = bernoulli_threshold(c.has_lockdown ? c.essential_workers_population : 0.0);
-    auto draw = [&](uint32_t agent, uint32_t slot) { return philox_draw(seed, agent, 0, DOM_INIT, slot); };
+    // init draws are keyed on the CREATION number, so an agent's attributes do not depend on how agents are numbered
+    auto draw = [&](uint32_t creation, uint32_t slot) { return philox_draw(seed, creation, 0, DOM_INIT, slot); };
 
     // Public-transport users are capped by the number of transport points Area::random_points can hand out
     // (grid.rs:96-101 "fix the hack", area.rs:64-74): ceil(sqrt(n as f32)) columns x rows clipped to the strip.
@@ -182,27 +251,70 @@ void build_population(const epi_config& c, const Geometry& g, uint64_t seed, int
     const size_t tw = (size_t)(g.transport.ex - g.transport.sx + 1), th = (size_t)(g.transport.ey - g.transport.sy + 1);
     const size_t pt_capacity = std::min(want_points, std::min(side, tw) * std::min(side, th));
 
+    // ---- the citizens in creation order (citizen_factory.rs:58-88 / Citizen::from_record citizen/mod.rs:155-180) ----
+    HostAgents made;
+    made.resize(n);
     size_t pt_users = 0;
-    for (uint32_t i = 0; i < n; ++i) {
-        const bool working = bernoulli(draw(i, IS_WORKING), thr_working);
-        const bool pt = bernoulli(draw(i, IS_PT), thr_pt) && working && pt_users < pt_capacity;
+    for (uint32_t cr = 0; cr < n; ++cr) {
+        bool working, pt;
+        if (records) {  // pub_transport is taken as it is
+            working = records->working[cr] != 0;
+            pt = records->pub_transport[cr] != 0;
+        } else {
+            working = bernoulli(draw(cr, IS_WORKING), thr_working);
+            pt = bernoulli(draw(cr, IS_PT), thr_pt) && working && pt_users < pt_capacity;
+        }
         if (pt) ++pt_users;
         uint32_t ws = WS_NA;
         if (working) {
-            ws = bernoulli(draw(i, IS_STAFF), thr_staff) ? WS_STAFF : WS_NORMAL;
-            if (ws == WS_NORMAL && bernoulli(draw(i, IS_ESSENTIAL), thr_essential)) ws = WS_ESSENTIAL;
+            ws = bernoulli(draw(cr, IS_STAFF), thr_staff) ? WS_STAFF : WS_NORMAL;
+            if (ws == WS_NORMAL && bernoulli(draw(cr, IS_ESSENTIAL), thr_essential)) ws = WS_ESSENTIAL;
         }
-        const uint32_t immunity_plus2 = (uint32_t)mulhi64(draw(i, IS_IMMUNITY), 5);
-        out.st[i] = ST_S | (immunity_plus2 << ST_IMM_SHIFT) | (pt ? ST_PT : 0u) | (ws << ST_WS_SHIFT) | (AK_HOME << ST_AREA_SHIFT);
-        out.t0[i] = 0;
-        const HouseSlot hs = house_slot(i, n, g.n_houses);
-        out.home[i] = house_origin(g, hs.house);
-        out.work[i] = working ? office_origin(g, hs.creation % g.n_offices) : 0u;
-        out.wsa[i] = ws == WS_STAFF ? kRoutineWorkTime : 0u;
+        const uint32_t immunity_plus2 = (uint32_t)mulhi64(draw(cr, IS_IMMUNITY), 5);
+        made.st[cr] = ST_S | (immunity_plus2 << ST_IMM_SHIFT) | (pt ? ST_PT : 0u) | (ws << ST_WS_SHIFT) | (AK_HOME << ST_AREA_SHIFT);
+        made.home[cr] = house_origin(g, cr % H);  // homes_iter.cycle() (grid.rs:108-113, 205-206)
+        made.work[cr] = working ? office_origin(g, cr % g.n_offices) : 0u;
+        made.wsa[cr] = ws == WS_STAFF ? kRoutineWorkTime : 0u;
+        // start cell: the k housemates of a house take the first k of (sx,sy),(sx,sy+1),(sx+1,sy),(sx+1,sy+1) in creation
+        // order; a lone occupant gets a uniformly random corner (area.rs:64-74)
+        const uint32_t house = cr % H, rank = cr / H;
+        const uint32_t housemates = (n - 1 - house) / H + 1;  // creation numbers house, house + H, ... < n
+        const int sx = g.housing.sx + 2 * (int)(house % (uint32_t)g.house_nx);
+        const int sy = g.housing.sy + 2 * (int)(house / (uint32_t)g.house_nx);
+        int x, y;
+        if (housemates == 1) {
+            x = sx + (int)mulhi64(draw(cr, IS_STARTX), 2);
+            y = sy + (int)mulhi64(draw(cr, IS_STARTY), 2);
+        } else {
+            x = sx + (int)(rank / 2);
+            y = sy + (int)(rank % 2);
+        }
+        made.cell[cr] = ((uint32_t)y << CELL_BITS) | (uint32_t)x;
+    }
+
+    // ---- agent numbering: id -> creation number ----
+    std::vector<uint32_t> creation_of(n);
+    {
+        const AgentOrder order = agent_order();
+        uint32_t i = 0;
+        if (order == AgentOrder::Creation) {
+            for (; i < n; ++i) creation_of[i] = i;
+        } else {
+            for (uint32_t house = 0; house < H && house < n; ++house)
+                for (uint32_t cr = house; cr < n; cr += H) creation_of[i++] = cr;
+        }
+        if (i != n) throw std::runtime_error("agent numbering: internal error");
+    }
+    out.resize(n);
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint32_t cr = creation_of[i];
+        out.cell[i] = made.cell[cr]; out.st[i] = made.st[cr]; out.t0[i] = 0; out.home[i] = made.home[cr]; out.work[i] = made.work[cr];
+        out.wsa[i] = made.wsa[cr];
         out.reg[i] = (uint32_t)region | ((uint32_t)region << 8);
     }
 
     // starting infections: uniform without replacement, then exposed / asymptomatic / mild / severe in that order
+    // (citizen_factory.rs:112-134)
     const uint32_t total = c.exposed + c.infected_mild_asymptomatic + c.infected_mild_symptomatic + c.infected_severe;
     std::vector<uint32_t> chosen;
     chosen.reserve(total);
@@ -222,25 +334,6 @@ void build_population(const epi_config& c, const Geometry& g, uint64_t seed, int
     infect(c.infected_mild_asymptomatic, ST_I, SEV_ASYM, 1);
     infect(c.infected_mild_symptomatic, ST_I, SEV_MILD, 1);
     infect(c.infected_severe, ST_I, SEV_SEVERE, 1);
-
-    // start cells: the k housemates of a house take the first k of (sx,sy),(sx,sy+1),(sx+1,sy),(sx+1,sy+1) in creation
-    // order; a lone occupant gets a uniformly random corner (area.rs:64-74)
-    const uint32_t H = g.n_houses;
-    for (uint32_t i = 0; i < n; ++i) {
-        const HouseSlot hs = house_slot(i, n, H);
-        const uint32_t house = hs.house, housemates = hs.housemates, rank = hs.rank;
-        const int sx = g.housing.sx + 2 * (int)(house % (uint32_t)g.house_nx);
-        const int sy = g.housing.sy + 2 * (int)(house / (uint32_t)g.house_nx);
-        int x, y;
-        if (housemates == 1) {
-            x = sx + (int)mulhi64(draw(i, IS_STARTX), 2);
-            y = sy + (int)mulhi64(draw(i, IS_STARTY), 2);
-        } else {
-            x = sx + (int)(rank / 2);
-            y = sy + (int)(rank % 2);
-        }
-        out.cell[i] = ((uint32_t)y << CELL_BITS) | (uint32_t)x;
-    }
 }
 
 }  // namespace epi

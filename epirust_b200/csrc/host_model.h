@@ -38,13 +38,9 @@ inline uint32_t office_index_of(const Geometry& g, uint32_t origin) {
     return (uint32_t)((y - g.work.sy) / 10 * g.office_nx + (x - g.work.sx) / 10);
 }
 
-// which house agent id i lives in (see the "Agent numbering" note in host_model.cpp)
-struct HouseSlot {
-    uint32_t house, rank, housemates;  // house index, position among its occupants, number of occupants
-    uint32_t creation;                 // the reference's creation number of this agent: house + rank * n_houses
-};
-bool house_major_order();
-HouseSlot house_slot(uint32_t agent, uint32_t n_agents, uint32_t n_houses);
+// how agent ids are assigned to the citizens of the population (see the "Agent numbering" note in host_model.cpp)
+enum class AgentOrder { Creation, House };
+AgentOrder agent_order();
 
 struct HostAgents {
     std::vector<uint32_t> cell, st, t0, home, work, wsa, reg;
@@ -52,9 +48,21 @@ struct HostAgents {
     void resize(size_t n) { cell.resize(n); st.resize(n); t0.resize(n); home.resize(n); work.resize(n); wsa.resize(n); reg.resize(n); }
 };
 
+// Population::Csv: the columns of the PopulationRecords the engine reads (citizen/population_record.rs:23-31, citizen/mod.rs:155-180),
+// in file order == the reference's creation order
+struct PopulationRecords {
+    std::vector<uint8_t> working, pub_transport;
+    size_t size() const { return working.size(); }
+};
+// csv::Reader::from_reader(file).deserialize::<PopulationRecord>() (grid.rs:202-208).  Throws std::runtime_error.
+PopulationRecords read_population_csv(const std::string& path);
+// `cfg` with number_of_agents resolved: the record count when cfg.population_csv_file is set (records are then loaded into `records`)
+epi_config resolve_population(const epi_config& cfg, PopulationRecords& records);
+
 // Grid::generate_population + citizen_factory + set_starting_infections + init_interventions' essential workers
 // (grid.rs:83-155, citizen_factory.rs:31-134, epidemiology_simulation.rs:178-192).  Throws std::runtime_error.
-void build_population(const epi_config& cfg, const Geometry& geo, uint64_t seed, int region, HostAgents& out);
+// With `records` (Population::Csv, Grid::read_population grid.rs:194-231) working / uses_public_transport come from the file.
+void build_population(const epi_config& cfg, const Geometry& geo, uint64_t seed, int region, HostAgents& out, const PopulationRecords* records = nullptr);
 
 // citizen_factory::update_commuters (citizen_factory.rs:90-110): the first sum(commute_row) working public-transport users
 // in creation order get the row's regions as work region (row order, commute_row[to] agents each)

@@ -365,38 +365,37 @@ __global__ void __launch_bounds__(256, KIND == KIND_MOVE ? EPI_MINB : 4) k_hour(
             if (((win.r[2] >> 8) & CELL_OCC_MASK) == 0) { tx = bx; ty = by; }  // target.get_random_point vacant -> go (citizen/mod.rs:387-392)
         } else if (mode == MODE_WALK) {  // Citizen::move_agent_from (citizen/mod.rs:415-432)
             const uint32_t cand = vacant_mask(hood_centre(win)) & valid_mask_inside(R, P.grid_size, bx, by);
-            if (cand) {
+            if (cand) {  // candidates.choose(rng): the k-th candidate in iterator order, k uniform
                 const int j = select_bit(cand, __umulhi(pick, (uint32_t)__popc(cand)));
                 ddx = hood_dx(j); ddy = hood_dy(j);
                 tx = bx + ddx; ty = by + ddy;
             }
         }
-        if (dynamics) {
-            // DiseaseStateMachine::next at the proposed cell (disease_state_machine.rs:53-70)
-            if (state == ST_S) {
-                if (scan) {  // on_susceptible, default_disease_handler.rs:64-86
-                    // the proposed cell is the window centre + (ddx, ddy), or the agent's own cell when the move was
-                    // not possible: a relocated walker / a goto that found its point occupied stays at (x, y), which
-                    // is outside the window -> second load (hours 7, 8, 16, 17 mostly)
-                    Hood hd;
-                    if (tx == bx + ddx && ty == by + ddy) hd = hood_at(win, ddx, ddy);
-                    else hd = hood_centre(load_window(grid, P, tx, ty));
-                    uint32_t inf = infectious_mask(hd);
-                    // neighbours are clipped to the NEW current_area: R is its rectangle unless a non-working agent's
-                    // area changed this hour (h = 8, 12), where R is still the old one
-                    if (inf) inf &= valid_mask(kind == kind0 ? R : rect_of(kind), P.grid_size, tx, ty);
-                    while (inf) {
-                        const int j = __ffs(inf) - 1;
-                        inf &= inf - 1u;
-                        const uint32_t b = ((j < 4 ? hd.lo : hd.hi) >> (8 * (j & 3))) & CELL_OCC_MASK;
-                        if (bernoulli(dr.expose(j), P.thr_rate[b - 1u])) {
-                            state = ST_E;
-                            D.t0[i] = hour;
-                            break;
-                        }
-                    }
+        if (scan) {  // on_susceptible at the proposed cell (disease_state_machine.rs:53-70, default_disease_handler.rs:64-86)
+            // the proposed cell is the window centre + (ddx, ddy), or the agent's own cell when the move was
+            // not possible: a relocated walker / a goto that found its point occupied stays at (x, y), which
+            // is outside the window -> second load (hours 7, 8, 16, 17 mostly)
+            Hood hd;
+            if (tx == bx + ddx && ty == by + ddy) hd = hood_at(win, ddx, ddy);
+            else hd = hood_centre(load_window(grid, P, tx, ty));
+            uint32_t inf = infectious_mask(hd);
+            // neighbours are clipped to the NEW current_area: R is its rectangle unless a non-working agent's
+            // area changed this hour (h = 8, 12), where R is still the old one
+            if (inf) inf &= valid_mask(kind == kind0 ? R : rect_of(kind), P.grid_size, tx, ty);
+            while (inf) {
+                const int j = __ffs(inf) - 1;
+                inf &= inf - 1u;
+                const uint32_t b = ((j < 4 ? hd.lo : hd.hi) >> (8 * (j & 3))) & CELL_OCC_MASK;
+                if (bernoulli(dr.expose(j), P.thr_rate[b - 1u])) {
+                    state = ST_E;
+                    D.t0[i] = hour;
+                    break;
                 }
-            } else if (state == ST_E) {  // on_exposed, :52-62
+            }
+        }
+        if (dynamics) {
+            // DiseaseStateMachine::next for the other states (disease_state_machine.rs:53-70)
+            if (state == ST_E && (s0 & ST_STATE_MASK) == ST_E) {  // on_exposed, :52-62
                 const int f = (int)__umulhi(factor, 3u) - 1;
                 if (hour - t0v >= (uint32_t)((int)P.exposed_duration + f)) {
                     const bool symptoms = bernoulli(a, P.thr_symptomatic);
@@ -434,8 +433,22 @@ __global__ void __launch_bounds__(256, KIND == KIND_MOVE ? EPI_MINB : 4) k_hour(
     st_stream(D.prop + i, prop);
 }
 
+// k_commit: four consecutive agents per thread.  The proposal and cell words arrive as two 128-bit loads, the (up to) four
+// claim words are requested together before anything is stored, so a warp has 4x the memory requests in flight of a
+// one-agent-per-thread version (the kernel is latency-bound: ~25 instructions per agent, two dependent round trips).
+#ifndef EPI_CPF
+#define EPI_CPF 0u  // L2 prefetch distance in agents (0: none -- with four agents per thread it no longer pays: 97 us vs 99-101 us)
+#endif
+__device__ __forceinline__ uint4 ld_stream4(const uint32_t* p) {
+    uint4 v;
+    asm volatile("ld.global.cs.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_stream4(uint32_t* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 __global__ void __launch_bounds__(256) k_commit(Params P, DevPtrs D, uint32_t hour_offset) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4u;
     const uint32_t hour = D.clock->hour_base + hour_offset;
     if (blockIdx.x == 0 && threadIdx.x < 32) {
         // the hour's Counts row = sum of the running totals' copies (all k_hour blocks of this hour have finished)
@@ -447,31 +460,63 @@ __global__ void __launch_bounds__(256) k_commit(Params P, DevPtrs D, uint32_t ho
             if (threadIdx.x == 0) D.counts[(size_t)(hour - D.clock->ring_base) * 8 + c] = v;
         }
     }
-    if (i >= P.n) return;
-    if ((threadIdx.x & 7u) == 0 && i + PREFETCH_AHEAD < P.n) {
-        prefetch_l2(D.prop + i + PREFETCH_AHEAD);
-        prefetch_l2(D.cell + i + PREFETCH_AHEAD);
+    if (i0 >= P.n) return;
+    if (EPI_CPF != 0u && (threadIdx.x & 1u) == 0 && i0 + EPI_CPF < P.n) {  // one prefetch per 32-byte sector
+        prefetch_l2(D.prop + i0 + EPI_CPF);
+        prefetch_l2(D.cell + i0 + EPI_CPF);
     }
-    const uint32_t prop = ld_early_rw(D.prop + i);
-    const uint32_t c0 = ld_early_rw(D.cell + i);  // issued with the prop load: one memory round trip
-    if (prop == 0) return;
-    const uint32_t byte = (prop >> PROP_BYTE_SHIFT) + 1u;
-    const size_t at = P.cell_offset(c0);
-    if (prop & PROP_MOVE) {
-        const uint32_t tc = prop & PROP_CELL_MASK;
-        const size_t tat = P.cell_offset(tc);
-        const uint32_t stamp = hour - D.clock->epoch_base + 1u;
-        const uint32_t id_mask = (1u << P.id_bits) - 1u;
-        const bool win = D.claim[tat] == ((stamp << P.id_bits) | (id_mask - i));  // lowest id among claimants: upcoming.entry(new).or_insert
-        if (win) {
-            D.grid[at] = 0;
-            D.grid[tat] = (uint8_t)byte;
-            st_stream(D.cell + i, tc);
-            return;
+    const bool full = i0 + 3u < P.n;  // P.n need not be a multiple of 4
+    uint32_t prop[4], c0[4];
+    if (full) {
+        const uint4 p4 = ld_stream4(D.prop + i0), c4 = ld_stream4(D.cell + i0);
+        prop[0] = p4.x; prop[1] = p4.y; prop[2] = p4.z; prop[3] = p4.w;
+        c0[0] = c4.x; c0[1] = c4.y; c0[2] = c4.z; c0[3] = c4.w;
+    } else {
+#pragma unroll
+        for (uint32_t j = 0; j < 4; ++j) {
+            const bool in = i0 + j < P.n;
+            prop[j] = in ? D.prop[i0 + j] : 0u;
+            c0[j] = in ? D.cell[i0 + j] : 0u;
         }
-        // lost: stays at old_cell (allocation_map.rs:99-102); still refresh the byte if it changed
     }
-    if (prop & PROP_DIRTY) D.grid[at] = (uint8_t)byte;
+    if ((prop[0] | prop[1] | prop[2] | prop[3]) == 0) return;
+    const uint32_t stamp = hour - D.clock->epoch_base + 1u;
+    const uint32_t id_mask = (1u << P.id_bits) - 1u;
+    // every claim word first: one round trip for the four agents
+    uint32_t cl[4];
+#pragma unroll
+    for (uint32_t j = 0; j < 4; ++j) {
+        cl[j] = 0;
+        if (prop[j] & PROP_MOVE) cl[j] = __ldcg(D.claim + P.cell_offset(prop[j] & PROP_CELL_MASK));
+    }
+    bool moved = false;
+#pragma unroll
+    for (uint32_t j = 0; j < 4; ++j) {
+        if (prop[j] == 0) continue;
+        const uint32_t byte = (prop[j] >> PROP_BYTE_SHIFT) + 1u;
+        const size_t at = P.cell_offset(c0[j]);
+        if (prop[j] & PROP_MOVE) {
+            const uint32_t tc = prop[j] & PROP_CELL_MASK;
+            // lowest id among the claimants: upcoming.entry(new).or_insert (allocation_map.rs:93-98)
+            if (cl[j] == ((stamp << P.id_bits) | (id_mask - (i0 + j)))) {
+                D.grid[at] = 0;
+                D.grid[P.cell_offset(tc)] = (uint8_t)byte;
+                c0[j] = tc;
+                moved = true;
+                continue;
+            }
+            // lost: stays at old_cell (allocation_map.rs:99-102); still refresh the byte if it changed
+        }
+        if (prop[j] & PROP_DIRTY) D.grid[at] = (uint8_t)byte;
+    }
+    if (moved) {
+        if (full) st_stream4(D.cell + i0, c0[0], c0[1], c0[2], c0[3]);
+        else {
+#pragma unroll
+            for (uint32_t j = 0; j < 4; ++j)
+                if (i0 + j < P.n) D.cell[i0 + j] = c0[j];
+        }
+    }
 }
 
 __global__ void __launch_bounds__(256) k_sleep(Params P, DevPtrs D, uint32_t hour_offset) {
@@ -588,7 +633,7 @@ void launch_hour(const Params& P, const DevPtrs& D, uint32_t hour_of_day, uint32
 }
 void launch_recount(const Params& P, const DevPtrs& D, cudaStream_t s) { k_recount<<<blocks_for(P.n), 256, 0, s>>>(P, D.st, D.tot); }
 void launch_set_clock(Clock* clock, const Clock& value, cudaStream_t s) { k_set_clock<<<1, 1, 0, s>>>(clock, value); }
-void launch_commit(const Params& P, const DevPtrs& D, uint32_t hour_offset, cudaStream_t s) { k_commit<<<blocks_for(P.n), 256, 0, s>>>(P, D, hour_offset); }
+void launch_commit(const Params& P, const DevPtrs& D, uint32_t hour_offset, cudaStream_t s) { k_commit<<<blocks_for((P.n + 3u) / 4u), 256, 0, s>>>(P, D, hour_offset); }
 void launch_sleep(const Params& P, const DevPtrs& D, uint32_t hour_offset, cudaStream_t s) { k_sleep<<<blocks_for(P.n), 256, 0, s>>>(P, D, hour_offset); }
 void launch_lock(const Params& P, const DevPtrs& D, cudaStream_t s) { k_lock<<<blocks_for(P.n), 256, 0, s>>>(P, D.st); }
 void launch_unlock(const Params& P, const DevPtrs& D, cudaStream_t s) { k_unlock<<<blocks_for(P.n), 256, 0, s>>>(P, D.st); }

@@ -149,7 +149,7 @@ int run_single_engine(epi_engine* e, const epi_config& cfg, RunResult& result, b
         const uint32_t last = result.rows.back().hour;
         std::printf("INFO - Number of iterations: %u, Total Time taken %f seconds\n", last, result.loop_seconds);
         std::printf("INFO - Iterations/sec: %f\n", (double)last / result.loop_seconds);
-        std::printf("INFO - Agent-steps/sec: %e\n", (double)last * (double)cfg.number_of_agents / result.loop_seconds);
+        std::printf("INFO - Agent-steps/sec: %e\n", (double)last * (double)epi_population(e) / result.loop_seconds);
     }
     static const char* names[3] = {"lockdown", "vaccination", "build_new_hospital"};
     for (const epi_intervention_event& ev : e->events) {
@@ -167,8 +167,11 @@ static void config_from_value(const JsonValue& root, epi_config& c) {
         c.number_of_agents = a->at("number_of_agents").as_u32("number_of_agents");
         c.public_transport_percentage = a->at("public_transport_percentage").as_number("public_transport_percentage");
         c.working_percentage = a->at("working_percentage").as_number("working_percentage");
-    } else if (pop.find("Csv")) {
-        throw std::runtime_error("population.Csv is not supported by the GPU engine yet (SURVEY.md section 8f row 3); use population.Auto");
+    } else if (const JsonValue* v = pop.find("Csv")) {  // CsvPopulation { file, cols } (population.rs:30-34)
+        const std::string file = v->at("file").as_string("file");
+        v->at("cols");  // required by serde; not read by the engine
+        if (file.empty() || file.size() >= EPI_PATH_MAX) throw std::runtime_error("population.Csv.file: empty or longer than " + std::to_string(EPI_PATH_MAX - 1) + " bytes");
+        std::memcpy(c.population_csv_file, file.c_str(), file.size() + 1);
     } else {
         throw std::runtime_error("unknown variant for `population`, expected `Csv` or `Auto`");
     }

@@ -25,8 +25,9 @@ DEFAULT_DISEASE = dict(
 
 
 def make_config(n_agents=10000, grid_size=250, hours=1080, exposed=1, asym=0, mild=0, severe=0,
-                pt=0.2, working=0.7, beds=0.003, lockdown=None, hospital=None, vaccinate=(), **disease):
-    """Build an EpiConfig; defaults are engine/config/default.json without its Lockdown intervention."""
+                pt=0.2, working=0.7, beds=0.003, lockdown=None, hospital=None, vaccinate=(), population_csv=None, **disease):
+    """Build an EpiConfig; defaults are engine/config/default.json without its Lockdown intervention.  population_csv:
+    path of a population file (Population::Csv) -- n_agents, pt and working are then ignored."""
     c = EpiConfig()
     c.number_of_agents = n_agents
     c.public_transport_percentage = pt
@@ -49,6 +50,8 @@ def make_config(n_agents=10000, grid_size=250, hours=1080, exposed=1, asym=0, mi
     for i, (h, p) in enumerate(vaccinate):
         c.vaccinate_at_hour[i] = h
         c.vaccinate_percent[i] = p
+    if population_csv:
+        c.population_csv_file = str(population_csv).encode()
     return c
 
 
@@ -266,13 +269,21 @@ class Engine:
         return int(self.L.epi_device_bytes(self.h))
 
 
-def build_population(cfg, seed=1):
-    """The Auto population factory on the host (epi_build_population; no GPU needed): dict of arrays like Engine.get_state()."""
+def population_size(cfg):
+    """Number of agents `cfg` describes: number_of_agents, or the number of records of its population CSV (host only)."""
     L = _ffi.load()
-    arrs = {f: np.zeros(cfg.number_of_agents, dt) for f, dt in zip(STATE_FIELDS, STATE_DTYPES)}
-    rc = L.epi_build_population(C.byref(cfg), seed, *[_ptr(arrs[f]) for f in STATE_FIELDS])
-    if rc != 0:
-        raise EpiError(f"epi_build_population failed with status {rc}")
+    n = C.c_uint32(0)
+    if L.epi_population_size(C.byref(cfg), C.byref(n)):
+        raise EpiError(L.epi_last_error(None).decode(errors="replace"))
+    return n.value
+
+
+def build_population(cfg, seed=1):
+    """The population factory on the host (epi_build_population; no GPU needed): dict of arrays like Engine.get_state()."""
+    L = _ffi.load()
+    arrs = {f: np.zeros(population_size(cfg), dt) for f, dt in zip(STATE_FIELDS, STATE_DTYPES)}
+    if L.epi_build_population(C.byref(cfg), seed, *[_ptr(arrs[f]) for f in STATE_FIELDS]):
+        raise EpiError(L.epi_last_error(None).decode(errors="replace"))
     return arrs
 
 

@@ -34,6 +34,7 @@ extern "C" {
 #define EPI_ERR_NCCL 6
 
 #define EPI_MAX_VACCINATIONS 8
+#define EPI_PATH_MAX 256
 #define EPI_DRAWS_PER_AGENT 16 /* u64 draw slots per agent-hour, see DESIGN.md "Draw slots" */
 
 /* common::config::Config for Population::Auto (common/src/config/mod.rs:44-58, population.rs:36-43,
@@ -60,6 +61,12 @@ typedef struct epi_config {
     int32_t n_vaccinations;
     uint32_t vaccinate_at_hour[EPI_MAX_VACCINATIONS];
     double vaccinate_percent[EPI_MAX_VACCINATIONS];
+    /* Population::Csv { file, cols } (common/src/config/population.rs:30-34): path of the population file, or "" for
+     * Population::Auto.  When set, epi_create* reads it like Grid::read_population (engine/src/geography/grid.rs:194-231):
+     * one PopulationRecord per line (columns ind, age, working, pub_transport; citizen/population_record.rs:23-31), record c
+     * gets house c % H and office c % O; number_of_agents and the two Auto percentages are ignored.  `cols` and
+     * `disease_overrides` are parsed and ignored, as in the reference. */
+    char population_csv_file[EPI_PATH_MAX];
 } epi_config;
 
 /* engine::models::events::Counts (engine/src/models/events/counts.rs:25-34): one epicurve CSV row. */
@@ -199,8 +206,11 @@ int epi_set_state(epi_engine* e, uint32_t n, const int32_t* cell_x, const int32_
                   const uint32_t* home, const uint32_t* work, const uint32_t* wsa);
 /* Host only (no GPU needed): the Auto population factory -- Grid::generate_population + citizen_factory +
  * set_starting_infections + the essential-worker draw of init_interventions (engine/src/geography/grid.rs:83-155,
- * citizen/citizen_factory.rs:31-134, epidemiology_simulation.rs:178-192) -- as the arrays epi_create uploads, in the
- * layout of epi_get_state.  Arrays of cfg->number_of_agents entries. */
+ * citizen/citizen_factory.rs:31-134, epidemiology_simulation.rs:178-192; Grid::read_population, grid.rs:194-231, when
+ * cfg->population_csv_file is set) -- as the arrays epi_create uploads, in the layout of epi_get_state.  Arrays of
+ * epi_population_size() entries. */
+/* Host only: the number of agents `cfg` describes -- number_of_agents, or the number of records of the population CSV. */
+int epi_population_size(const epi_config* cfg, uint32_t* n);
 int epi_build_population(const epi_config* cfg, uint64_t seed, int32_t* cell_x, int32_t* cell_y, uint32_t* st, uint32_t* t0,
                          uint32_t* home, uint32_t* work, uint32_t* wsa);
 /* out[0..3] housing sx,sy,ex,ey; [4..7] transport; [8..11] work; [12..15] hospital (current); [16] houses; [17] offices;

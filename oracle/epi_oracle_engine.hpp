@@ -10,6 +10,7 @@
 #include <cstdlib>
 
 #include <map>
+#include <tuple>
 #include <unordered_set>
 
 #include "epi_oracle.hpp"
@@ -44,7 +45,83 @@ extern "C" struct orc_config {
     int32_t n_vaccinations;
     uint32_t vaccinate_at_hour[8];
     double vaccinate_percent[8];
+    // population.Csv.file (population.rs:30-34), "" for population.Auto
+    char population_csv_file[256];
 };
+
+// PopulationRecord (citizen/population_record.rs:23-43) as read by csv::Reader::deserialize in Grid::read_population
+// (grid.rs:202-208): header row, columns matched by name (ind: u32, age: String, working / pub_transport: "True" | "False").
+struct PopulationRecord {
+    uint32_t ind;
+    std::string age;
+    bool working, pub_transport;
+};
+inline std::vector<PopulationRecord> read_population_records(const std::string& path) {
+    FILE* f = std::fopen(path.c_str(), "rb");
+    if (!f) throw std::runtime_error("Could not read population file");
+    std::string text;
+    char buf[1 << 16];
+    size_t got;
+    while ((got = std::fread(buf, 1, sizeof buf, f)) > 0) text.append(buf, got);
+    std::fclose(f);
+    // tokenise: records end at \n (or \r\n), fields at ',', a field may be wrapped in double quotes ("" = a quote)
+    std::vector<std::vector<std::string>> table;
+    std::vector<std::string> row;
+    std::string field;
+    bool in_quotes = false, any = false;
+    auto end_field = [&] { row.push_back(field); field.clear(); };
+    auto end_row = [&] {
+        end_field();
+        if (!(row.size() == 1 && row[0].empty())) table.push_back(row);  // blank lines are skipped
+        row.clear();
+        any = false;
+    };
+    for (size_t i = 0; i < text.size(); ++i) {
+        const char ch = text[i];
+        if (in_quotes) {
+            if (ch == '"' && i + 1 < text.size() && text[i + 1] == '"') { field.push_back('"'); ++i; }
+            else if (ch == '"') in_quotes = false;
+            else field.push_back(ch);
+            continue;
+        }
+        if (ch == '"' && field.empty()) { in_quotes = true; any = true; }
+        else if (ch == ',') { end_field(); any = true; }
+        else if (ch == '\n') end_row();
+        else if (ch == '\r' && i + 1 < text.size() && text[i + 1] == '\n') continue;
+        else { field.push_back(ch); any = true; }
+    }
+    if (in_quotes) throw std::runtime_error("Could not deserialize population line: unterminated quote");
+    if (any || !field.empty() || !row.empty()) end_row();
+    if (table.empty()) return {};
+    const std::vector<std::string>& header = table[0];
+    auto column = [&](const char* name) {
+        for (size_t k = 0; k < header.size(); ++k) if (header[k] == name) return k;
+        throw std::runtime_error(std::string("Could not deserialize population line: missing field `") + name + "`");
+    };
+    const size_t c_ind = column("ind"), c_age = column("age"), c_working = column("working"), c_pt = column("pub_transport");
+    auto to_bool = [](const std::string& v) {
+        if (v == "True") return true;
+        if (v == "False") return false;
+        throw std::runtime_error("Could not deserialize population line: expected True or False, got \"" + v + "\"");
+    };
+    std::vector<PopulationRecord> out;
+    for (size_t r = 1; r < table.size(); ++r) {
+        const std::vector<std::string>& rec = table[r];
+        if (rec.size() != header.size()) throw std::runtime_error("Could not deserialize population line: unequal record lengths");
+        PopulationRecord pr;
+        const std::string& ind = rec[c_ind];
+        if (ind.empty() || ind.size() > 10) throw std::runtime_error("Could not deserialize population line: bad `ind`");
+        uint64_t v = 0;
+        for (char d : ind) { if (d < '0' || d > '9') throw std::runtime_error("Could not deserialize population line: bad `ind`"); v = v * 10 + (uint64_t)(d - '0'); }
+        if (v > 0xFFFFFFFFull) throw std::runtime_error("Could not deserialize population line: bad `ind`");
+        pr.ind = (uint32_t)v;
+        pr.age = rec[c_age];
+        pr.working = to_bool(rec[c_working]);
+        pr.pub_transport = to_bool(rec[c_pt]);
+        out.push_back(pr);
+    }
+    return out;
+}
 
 inline Disease disease_from(const orc_config& c) {
     Disease d;
@@ -143,6 +220,8 @@ struct InterventionEvent {  // listeners/intervention_reporter.rs:28-33
 // -----------------------------------------------------------------------------
 struct Engine {
     orc_config cfg;
+    std::vector<PopulationRecord> records;  // Population::Csv only
+    std::vector<uint32_t> creation_of;      // agent id -> the reference's creation number (init draws are keyed on it)
     Disease disease;
     CitizenLocationMap map;
     Counts counts_at_hr;
@@ -174,6 +253,12 @@ struct Engine {
     // Epidemiology::new (epidemiology_simulation.rs:75-135) for Population::Auto
     void init(const orc_config& c, uint64_t seed_, Rng::Mode mode_, int threads_) {
         cfg = c; seed = seed_; mode = mode_; threads = std::max(1, threads_);
+        cfg.population_csv_file[sizeof(cfg.population_csv_file) - 1] = 0;
+        records.clear();
+        if (cfg.population_csv_file[0]) {  // Population::Csv (epidemiology_simulation.rs:91)
+            records = read_population_records(cfg.population_csv_file);
+            cfg.number_of_agents = (uint32_t)records.size();
+        }
         disease = disease_from(c);
         streams.clear();
         for (int t = 0; t <= threads; ++t) streams.emplace_back(seed * 0x9E3779B97F4A7C15ull + 0x1234567ull * (uint64_t)(t + 1));
@@ -199,7 +284,7 @@ struct Engine {
             if (!map.current_locations.used[i]) continue;
             Citizen& z = map.current_locations.vals[i];
             if (z.work_status == Normal) {  // Citizen::assign_essential_worker citizen/mod.rs:434-440
-                Rng r = engine_rng(z.id, 0, DOM_INIT);
+                Rng r = engine_rng(creation_of[z.id], 0, DOM_INIT);
                 if (r.gen_bool(IS_ESSENTIAL, ess)) z.work_status = Essential;
             }
         }
@@ -208,40 +293,31 @@ struct Engine {
 
     // Grid::generate_population (grid.rs:83-123) + citizen_factory (citizen_factory.rs:31-88)
     // + set_start_locations_and_occupancies (grid.rs:125-155)
+    // With records (Population::Csv): Grid::read_population (grid.rs:194-231) + Citizen::from_record (citizen/mod.rs:155-180):
+    // record c gets houses.cycle()[c] / offices.cycle()[c]; working and uses_public_transport come from the file.
     void generate_population(Grid& grid, std::vector<Point>& home_loc, std::vector<Citizen>& agents) {
+        const bool from_csv = cfg.population_csv_file[0] != 0;
         const uint32_t n = cfg.number_of_agents;
+        if (from_csv && (size_t)n > (size_t)(constants::HOME_SIZE * constants::HOME_SIZE) * grid.houses.size())
+            throw std::runtime_error("Cannot accommodate citizens into homes!");  // grid.rs:216-223
         if (grid.houses.empty() || grid.offices.empty()) throw std::runtime_error("grid too small: no houses or offices");
         double n_pt = (double)n * (cfg.public_transport_percentage + 0.1) * (cfg.working_percentage + 0.1);  // grid.rs:98-99
         size_t n_transport_locations = random_points_len(grid.transport_area, (size_t)std::ceil(n_pt));
-        agents.resize(n);
         size_t pt_users = 0;
         const size_t H = grid.houses.size(), O = grid.offices.size();
-        // Agent numbering (a convention shared with the engine under test, not reference behaviour): the reference gives
-        // the agent it creates as number c the house c % H and the office c % O (grid.rs:108-113); ids are opaque Uuids.
-        // Agent id i here is the rank-th occupant of house house_of[i], i.e. the reference's creation number
-        // c = house + rank * H -- the same population, numbered house by house.  EPI_AGENT_ORDER=creation: id == c.
-        const char* order_env = getenv("EPI_AGENT_ORDER");
-        const bool by_house = !(order_env && std::string(order_env) == "creation");
-        std::vector<uint32_t> house_of(n), rank_of(n);
-        {
-            uint32_t i = 0;
-            if (by_house) {
-                for (uint32_t h = 0; h < H && i < n; ++h)
-                    for (uint32_t c = h, k = 0; c < n; c += (uint32_t)H, ++k) { house_of[i] = h; rank_of[i] = k; ++i; }
-            } else {
-                for (; i < n; ++i) { house_of[i] = i % (uint32_t)H; rank_of[i] = i / (uint32_t)H; }
-            }
-        }
-        for (uint32_t i = 0; i < n; ++i) {  // create_citizen citizen_factory.rs:58-88
-            Rng r = engine_rng(i, 0, DOM_INIT);
-            bool is_working = r.gen_bool(IS_WORKING, cfg.working_percentage);
-            const uint32_t creation = house_of[i] + rank_of[i] * (uint32_t)H;
-            Area home = grid.houses[house_of[i]];
-            Area work = grid.offices[creation % O];
-            bool uses_pt = r.gen_bool(IS_PT, cfg.public_transport_percentage) && is_working && pt_users < n_transport_locations;
+        // The citizens in the reference's creation order: number c gets houses[c % H] and offices[c % O] (grid.rs:108-113,
+        // 205-206).  Init draws are keyed on c.
+        std::vector<Citizen> made(n);
+        for (uint32_t c = 0; c < n; ++c) {  // create_citizen citizen_factory.rs:58-88 / Citizen::from_record citizen/mod.rs:155-180
+            Rng r = engine_rng(c, 0, DOM_INIT);
+            bool is_working = from_csv ? records[c].working : r.gen_bool(IS_WORKING, cfg.working_percentage);
+            Area home = grid.houses[c % H];
+            Area work = grid.offices[c % O];
+            bool uses_pt = from_csv ? records[c].pub_transport
+                                    : r.gen_bool(IS_PT, cfg.public_transport_percentage) && is_working && pt_users < n_transport_locations;
             if (uses_pt) pt_users++;
             Citizen z;
-            z.id = i;
+            z.id = c;
             z.home_location = home;
             z.work_location = is_working ? work : home;
             z.transport_location = home.start_offset;  // never read on the hot path (grid.rs:202 TODO in reference)
@@ -252,7 +328,44 @@ struct Engine {
             z.work_start_at = constants::ROUTINE_WORK_TIME;
             z.immunity = constants::IMMUNITY_RANGE[r.choose_index(IS_IMMUNITY, 5)];  // :210-213
             z.current_area = home;
-            agents[i] = z;
+            made[c] = z;
+        }
+        // start locations: Area::random_points(k) inside each agent's own house (area.rs:64-74).
+        // k>=2 -> both xs and both ys are chosen (order preserved), x outer / y inner, take k; k==1 -> one random x, one random y.
+        std::vector<uint8_t> per_house(H, 0);
+        for (uint32_t c = 0; c < n; ++c) {
+            if (per_house[c % H] >= constants::HOME_SIZE * constants::HOME_SIZE)
+                throw std::runtime_error("There are more agents assigned to a house than house capacity");  // grid.rs:140-142
+            per_house[c % H]++;
+        }
+        std::vector<Point> made_loc(n);
+        for (uint32_t c = 0; c < n; ++c) {
+            const Area& home = made[c].home_location;
+            const uint32_t k = per_house[c % H], j = c / (uint32_t)H;
+            if (k == 1) {
+                Rng r = engine_rng(c, 0, DOM_INIT);
+                int x = home.start_offset.x + (int)r.choose_index(IS_STARTX, 2);
+                int y = home.start_offset.y + (int)r.choose_index(IS_STARTY, 2);
+                made_loc[c] = Point{x, y};
+            } else {
+                made_loc[c] = Point{home.start_offset.x + (int)(j / 2), home.start_offset.y + (int)(j % 2)};
+            }
+        }
+        // Agent numbering -- a convention shared with the engine under test, not reference behaviour (the reference's ids
+        // are opaque Uuids): ids follow (house, creation number), i.e. the population is numbered house by house.
+        // EPI_AGENT_ORDER=creation keeps id == creation number.
+        const char* order_env = getenv("EPI_AGENT_ORDER");
+        creation_of.resize(n);
+        for (uint32_t c = 0; c < n; ++c) creation_of[c] = c;
+        if (!(order_env && std::string(order_env) == "creation"))
+            std::stable_sort(creation_of.begin(), creation_of.end(),
+                             [&](uint32_t x, uint32_t y) { return std::make_tuple(x % (uint32_t)H, x / (uint32_t)H) < std::make_tuple(y % (uint32_t)H, y / (uint32_t)H); });
+        agents.resize(n);
+        home_loc.resize(n);
+        for (uint32_t i = 0; i < n; ++i) {
+            agents[i] = made[creation_of[i]];
+            agents[i].id = i;
+            home_loc[i] = made_loc[creation_of[i]];
         }
         // set_starting_infections citizen_factory.rs:112-134 : choose_multiple (uniform, without replacement)
         Count total = cfg.exposed + cfg.infected_mild_asymptomatic + cfg.infected_mild_symptomatic + cfg.infected_severe;
@@ -269,27 +382,6 @@ struct Engine {
         for (Count j = 0; j < cfg.infected_mild_asymptomatic; ++j) agents[chosen[q++]].state_machine.state = State::infected(1, Asymptomatic);
         for (Count j = 0; j < cfg.infected_mild_symptomatic; ++j) agents[chosen[q++]].state_machine.state = State::infected(1, Mild);
         for (Count j = 0; j < cfg.infected_severe; ++j) agents[chosen[q++]].state_machine.state = State::infected(1, Severe);
-        // start locations: Area::random_points(k) inside each agent's own house (area.rs:64-74).
-        // k>=2 -> both xs and both ys are chosen (order preserved), x outer / y inner, take k; k==1 -> one random x, one random y.
-        std::vector<uint8_t> per_house(H, 0);
-        for (uint32_t i = 0; i < n; ++i) {
-            if (per_house[house_of[i]] >= constants::HOME_SIZE * constants::HOME_SIZE)
-                throw std::runtime_error("There are more agents assigned to a house than house capacity");  // grid.rs:140-142
-            per_house[house_of[i]]++;
-        }
-        home_loc.resize(n);
-        for (uint32_t i = 0; i < n; ++i) {
-            const Area& home = agents[i].home_location;
-            uint32_t k = per_house[house_of[i]], j = rank_of[i];
-            if (k == 1) {
-                Rng r = engine_rng(i, 0, DOM_INIT);
-                int x = home.start_offset.x + (int)r.choose_index(IS_STARTX, 2);
-                int y = home.start_offset.y + (int)r.choose_index(IS_STARTY, 2);
-                home_loc[i] = Point{x, y};
-            } else {
-                home_loc[i] = Point{home.start_offset.x + (int)(j / 2), home.start_offset.y + (int)(j % 2)};
-            }
-        }
     }
 
     // CitizenLocationMap::simulate (allocation_map.rs:67-129), standalone (travel_plan_config == None)

@@ -96,19 +96,19 @@ struct RegionEngine : Engine {
         region = region_;
         plan = plan_;
         Engine::init(c, seed_, Rng::KEYED, threads_);
-        capacity = c.number_of_agents + extra_capacity;
+        capacity = cfg.number_of_agents + extra_capacity;
         free_slots.clear();
-        for (uint32_t s = capacity; s-- > c.number_of_agents;) free_slots.push_back(s);  // pop order: n, n+1, ...
+        for (uint32_t s = capacity; s-- > cfg.number_of_agents;) free_slots.push_back(s);  // pop order: n, n+1, ...
         // update_commuters (citizen_factory.rs:90-110): the first sum(row) working public-transport users in creation order
         // get the regions of the commute row as work region, row order, `count` agents each
-        std::vector<Citizen*> by_id(c.number_of_agents, nullptr);
+        std::vector<Citizen*> by_id(cfg.number_of_agents, nullptr);
         PointMap& m = map.current_locations;
         for (size_t i = 0; i < m.capacity(); ++i) if (m.used[i]) by_id[m.vals[i].id] = &m.vals[i];
         if (plan && plan->commute_enabled) {
             uint32_t a = 0;
             for (int to = 0; to < plan->n_regions; ++to) {
                 uint32_t want = plan->get_outgoing(plan->commute, region, to);
-                while (want > 0 && a < c.number_of_agents) {
+                while (want > 0 && a < cfg.number_of_agents) {
                     Citizen& z = *by_id[a++];
                     if (z.is_working() && z.work_location.location_id == region && z.uses_public_transport) {
                         z.work_location.location_id = to;
@@ -122,7 +122,7 @@ struct RegionEngine : Engine {
         houses_occupancy.init(map.grid.houses);
         offices_occupancy.init(map.grid.offices);
         std::vector<uint32_t> hc(map.grid.houses.size(), 0), oc(map.grid.offices.size(), 0);
-        for (uint32_t a = 0; a < c.number_of_agents; ++a) {
+        for (uint32_t a = 0; a < cfg.number_of_agents; ++a) {
             const Citizen& z = *by_id[a];
             hc[house_index(map.grid, z.home_location)]++;
             if (z.is_working() && z.work_location.location_id == region) oc[office_index(map.grid, z.work_location)]++;

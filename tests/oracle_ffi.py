@@ -48,6 +48,7 @@ class EpiConfig(C.Structure):
         ("n_vaccinations", C.c_int32),
         ("vaccinate_at_hour", C.c_uint32 * 8),
         ("vaccinate_percent", C.c_double * 8),
+        ("population_csv_file", C.c_char * 256),
     ]
 
 
@@ -62,7 +63,7 @@ DEFAULT_DISEASE = dict(
 
 
 def make_config(n_agents=10000, grid_size=250, hours=1080, exposed=1, asym=0, mild=0, severe=0,
-                pt=0.2, working=0.7, beds=0.003, lockdown=None, hospital=None, vaccinate=(), **disease):
+                pt=0.2, working=0.7, beds=0.003, lockdown=None, hospital=None, vaccinate=(), population_csv=None, **disease):
     c = EpiConfig()
     c.number_of_agents = n_agents
     c.public_transport_percentage = pt
@@ -85,6 +86,8 @@ def make_config(n_agents=10000, grid_size=250, hours=1080, exposed=1, asym=0, mi
     for i, (h, p) in enumerate(vaccinate):
         c.vaccinate_at_hour[i] = h
         c.vaccinate_percent[i] = p
+    if population_csv:
+        c.population_csv_file = str(population_csv).encode()
     return c
 
 

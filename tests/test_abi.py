@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layout_matches_header():
     assert C.sizeof(_ffi.EpiCounts) == 28
-    assert C.sizeof(_ffi.EpiConfig) == 264
+    assert C.sizeof(_ffi.EpiConfig) == 264 + 256  # + population_csv_file[EPI_PATH_MAX]
 
 
 def test_default_json_parses_like_serde():
@@ -61,9 +61,16 @@ def test_starting_infections_default_and_errors():
     del base["starting_infections"]
     c = config_from_json_string(json.dumps(base))
     assert (c.exposed, c.infected_severe) == (1, 0)  # StartingInfections::default (starting_infections.rs:65-69)
+    csv = dict(base)  # Population::Csv (common/src/config/population.rs:30-34, fixture shape of common/config/test/csv_pop.json)
+    csv["population"] = {"Csv": {"file": "config/pune_population.csv", "cols": ["age", "sex", "working", "pub_transport"]}}
+    c = config_from_json_string(json.dumps(csv))
+    assert c.population_csv_file == b"config/pune_population.csv" and c.number_of_agents == 0
     bad = dict(base)
-    bad["population"] = {"Csv": {"file": "x.csv", "cols": []}}
-    with pytest.raises(ValueError, match="Csv"):
+    bad["population"] = {"Csv": {"file": "x.csv"}}  # serde: missing field `cols`
+    with pytest.raises(ValueError, match="cols"):
+        config_from_json_string(json.dumps(bad))
+    bad["population"] = {"Grid": {}}
+    with pytest.raises(ValueError, match="unknown variant"):
         config_from_json_string(json.dumps(bad))
     bad = dict(base)
     bad["interventions"] = [{"Curfew": {}}]

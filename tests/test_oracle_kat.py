@@ -262,14 +262,9 @@ def test_population_invariants():
     assert (s["cell_x"] >= g[0]).all() and (s["cell_x"] <= g[2]).all()
     ws = (s["st"] >> 13) & 3
     assert 0.6 < (ws != 3).mean() < 0.8  # working_percentage 0.7
-    # grid.rs:108-113: the agent created as number c gets house c % H and office c % O.  Agent ids are numbered house by
-    # house (DESIGN.md "Agent numbering"): the k-th occupant of house h is the reference's agent c = h + k * H.
-    home, H, n_off = s["home"].astype(np.int64), int(g[16]), int(g[17])
-    assert (np.diff(home) >= 0).all()
-    rank = np.arange(5000) - np.searchsorted(home, home, side="left")
-    creation = home + rank * H
-    assert sorted(creation.tolist()) == list(range(5000))
-    assert (s["work"][ws != 3] == (creation % n_off)[ws != 3]).all()
+    from test_population_host import check_numbering
+
+    check_numbering(s, 5000, int(g[16]), int(g[17]))
 
 
 def test_oracle_default_json_run_is_deterministic_and_conserves_population():

@@ -36,7 +36,8 @@ def test_exchange_conserves_agents_and_counts():
     R = 3
     mig = np.array([[0, 40, 20], [30, 0, 10], [25, 15, 0]], np.uint32)
     com = np.array([[0, 30, 10], [20, 0, 15], [5, 25, 0]], np.uint32)
-    m = O.OracleMultiEngine(_cfgs(R), seed=5, migration=mig, commute=com, start_migration_hour=20, end_migration_hour=150, extra_capacity=600, threads=2)
+    # no symptomatic agents on day 1, so every planned commuter can_move (citizen/mod.rs:452-454, 488-495)
+    m = O.OracleMultiEngine(_cfgs(R, mild=0, severe=0), seed=5, migration=mig, commute=com, start_migration_hour=20, end_migration_hour=150, extra_capacity=600, threads=2)
     total0 = sum(m.population(r) for r in range(R))
     pops = []
     for hour in range(1, 24 * 4 + 1):
