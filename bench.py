@@ -212,7 +212,7 @@ def run_ours(args):
     stream = torch.cuda.Stream()
     multi = world > 1
     plan = travel_plan_for(world, n) if multi else None
-    eng = Engine(cfg, seed=1 + rank, device=local, region=rank if multi else 0, plan=plan, extra_capacity=n // 25 if multi else 0)
+    eng = Engine(cfg, seed=1 + rank, device=local, region=rank if multi else 0, plan=plan, extra_capacity=max(32768, 2 * (world - 1) * (n // 1000 + n // 2000)) if multi else 0)
     eng.set_stream(stream.cuda_stream)
     runner = None
 

@@ -71,7 +71,7 @@ class EpiCounts(C.Structure):
 EXPORTS = [
     "epi_create", "epi_create_region", "epi_create_multi", "epi_destroy", "epi_last_error", "epi_population", "epi_capacity", "epi_counts_at_start",
     "epi_set_stream", "epi_travel_pack", "epi_travel_unpack", "epi_finish_hour", "epi_get_regions",
-    "epi_sync", "epi_reset", "epi_step", "epi_enqueue_hour", "epi_step_with_draws", "epi_run_hours", "epi_simulate_hours", "epi_intervention_events", "epi_lock_city", "epi_unlock_city", "epi_vaccinate",
+    "epi_sync", "epi_reset", "epi_step", "epi_enqueue_hour", "epi_enqueue_hours", "epi_collect_hours", "epi_next_decision_hour", "epi_step_with_draws", "epi_run_hours", "epi_simulate_hours", "epi_intervention_events", "epi_lock_city", "epi_unlock_city", "epi_vaccinate",
     "epi_expand_hospital", "epi_get_state", "epi_set_state", "epi_build_population", "epi_population_size", "epi_geometry", "epi_get_grid", "epi_set_kernel_timing",
     "epi_get_kernel_times", "epi_launch_count", "epi_device_bytes", "epi_config_from_json", "epi_config_from_json_string",
     "epi_run_standalone", "epi_version",
@@ -112,6 +112,10 @@ def load():
     L.epi_reset.argtypes = [vp]
     L.epi_step.argtypes = [vp, u32, C.POINTER(EpiCounts)]
     L.epi_enqueue_hour.argtypes = [vp, u32]
+    L.epi_enqueue_hours.argtypes = [vp, u32, u32]
+    L.epi_collect_hours.argtypes = [vp, vp, u32, C.POINTER(u32)]
+    L.epi_next_decision_hour.argtypes = [vp, u32]
+    L.epi_next_decision_hour.restype = u32
     L.epi_step_with_draws.argtypes = [vp, u32, vp, C.POINTER(EpiCounts)]
     L.epi_run_hours.argtypes = [vp, u32, u32, vp]
     L.epi_simulate_hours.argtypes = [vp, u32, u32, i32, vp, C.POINTER(u32), C.POINTER(i32)]

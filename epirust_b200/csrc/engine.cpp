@@ -110,6 +110,9 @@ void drop_graph(epi_engine* e) {
         cudaGraphExecDestroy(e->day_graph);
         e->day_graph = nullptr;
     }
+    for (auto& g : e->segment_graphs)
+        if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
+    e->segment_graphs.clear();
 }
 
 // enqueue one simulated hour (kernels only).  `inject`: draws table already on device.
@@ -185,8 +188,133 @@ void row_to_counts(const uint32_t* row, uint32_t hour, epi_counts* out) {
     out->hospitalized = row[3]; out->recovered = row[4]; out->deceased = row[5];
 }
 
+// ---- queued hours (multi-region days without intermediate host waits) ---------------------------------------------------
+// Capture hours [first, first + n) (n <= 24, no exchange inside) once per (hour of day, n); the device-resident Clock carries
+// the absolute hour and the ring base, so the same graph serves every day.
+int segment_graph(epi_engine* e, uint32_t first_hour, uint32_t n, epi_engine::SegmentGraph** out) {
+    const uint32_t key = (first_hour % 24u) * 32u + n;
+    for (auto& g : e->segment_graphs)
+        if (g.first == key) { *out = &g.second; return EPI_OK; }
+    epi_engine::SegmentGraph sg;
+    cudaGraph_t graph = nullptr;
+    const uint64_t launches0 = e->launches;
+    uint64_t kl0[EPI_N_KERNEL_KINDS];
+    memcpy(kl0, e->kernel_launches, sizeof(kl0));
+    CU(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+    bool sleep_done = false;
+    for (uint32_t off = 0; off < n; ++off) {
+        const uint32_t h = (first_hour + off) % 24u;
+        const bool is_sleep = h >= 1 && h <= 6;
+        enqueue_hour(e, first_hour + off, off, false, is_sleep && sleep_done);
+        sleep_done = is_sleep;
+    }
+    cudaError_t r = cudaStreamEndCapture(e->stream, &graph);
+    sg.launches = (uint32_t)(e->launches - launches0);
+    sg.n_sleep = (uint32_t)(e->kernel_launches[KK_SLEEP] - kl0[KK_SLEEP]);
+    sg.n_active = (uint32_t)(e->kernel_launches[KK_HOUR] - kl0[KK_HOUR]);
+    sg.n_scan = (uint32_t)(e->kernel_launches[KK_SCAN] - kl0[KK_SCAN]);
+    e->launches = launches0;
+    memcpy(e->kernel_launches, kl0, sizeof(kl0));
+    if (r != cudaSuccess) return engine_fail(e, EPI_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(r));
+    r = cudaGraphInstantiate(&sg.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (r != cudaSuccess) return engine_fail(e, EPI_ERR_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(r));
+    e->segment_graphs.emplace_back(key, sg);
+    *out = &e->segment_graphs.back().second;
+    return EPI_OK;
+}
+
+// append hours [first, first + n) to the queue; exchange_hour: the single hour of an exchange (its kernels only)
+int queue_hours(epi_engine* e, uint32_t first_hour, uint32_t n, bool exchange_hour) {
+    if (n == 0) return EPI_OK;
+    if (!e->pend_kind.empty() && e->pend_kind.back() == 2) return engine_fail(e, EPI_ERR_STATE, "an exchange hour is queued: epi_collect_hours / epi_finish_hour first");
+    if (!e->pend_kind.empty() && first_hour != e->pend_first + (uint32_t)e->pend_kind.size())
+        return engine_fail(e, EPI_ERR_STATE, "queued hours must be consecutive");
+    if (e->pend_kind.size() + n > RING_ROWS) return engine_fail(e, EPI_ERR_STATE, "too many queued hours: call epi_collect_hours");
+    if (e->pend_kind.empty()) e->pend_first = first_hour;
+    const uint32_t row0 = first_hour - e->pend_first;
+    CU(cudaMemsetAsync(e->D.counts + (size_t)row0 * 8, 0, (size_t)n * 8 * sizeof(uint32_t), e->stream));
+    int rc = ensure_epoch(e, first_hour, first_hour + n - 1);
+    if (rc) return rc;
+    uint32_t off = 0;
+    while (off < n) {
+        const uint32_t hour = first_hour + off;
+        const uint32_t len = std::min(n - off, 24u);
+        {
+            Timed t(e, KK_MISC);
+            launch_set_clock(e->d_clock, Clock{hour, e->epoch_base, e->pend_first, 0}, e->stream);
+        }
+        if (!exchange_hour && !e->timing && e->graphs_enabled) {
+            epi_engine::SegmentGraph* sg = nullptr;
+            rc = segment_graph(e, hour, len, &sg);
+            if (rc) return rc;
+            CU(cudaGraphLaunch(sg->exec, e->stream));
+            e->launches += sg->launches;
+            e->kernel_launches[KK_SLEEP] += sg->n_sleep; e->kernel_launches[KK_HOUR] += sg->n_active; e->kernel_launches[KK_COMMIT] += sg->n_active;
+            e->kernel_launches[KK_SCAN] += sg->n_scan;
+        }
+        bool sleep_done = false;
+        for (uint32_t k = 0; k < len; ++k) {
+            const uint32_t h = (hour + k) % 24u;
+            const bool is_sleep = h >= 1 && h <= 6;
+            if (exchange_hour || e->timing || !e->graphs_enabled) {
+                rc = enqueue_hour(e, hour + k, k, false, is_sleep && sleep_done);
+                if (rc) return rc;
+            }
+            e->pend_kind.push_back(exchange_hour ? 2 : (is_sleep && sleep_done ? 0 : 1));
+            e->pend_population.push_back(e->population);
+            sleep_done = is_sleep;
+        }
+        off += len;
+    }
+    e->have_last_row = e->have_last_row && !exchange_hour;
+    CU(cudaGetLastError());
+    return EPI_OK;
+}
+
+// wait for the queued hours and turn their ring rows into Counts (the per-row checks of run_chunk); exchange rows are left out
+int collect_hours(epi_engine* e, std::vector<epi_counts>& rows) {
+    rows.clear();
+    const uint32_t n = (uint32_t)e->pend_kind.size();
+    if (n == 0) return EPI_OK;
+    CU(cudaMemcpyAsync(e->h_counts, e->D.counts, (size_t)n * 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    if (e->timing) drain_events(e);
+    const std::vector<uint8_t> kind = e->pend_kind;
+    const std::vector<uint32_t> population = e->pend_population;
+    const uint32_t first_hour = e->pend_first;
+    e->pend_kind.clear();
+    e->pend_population.clear();
+    for (uint32_t k = 0; k < n; ++k) {
+        if (kind[k] == 2) continue;
+        if (kind[k] == 1) {
+            const epi_counts prev = e->last_counts;
+            row_to_counts(e->h_counts + (size_t)k * 8, first_hour + k, &e->last_counts);
+            const uint32_t h = (first_hour + k) % 24u;
+            if (h >= 1 && h <= 6 && e->have_last_row) {
+                const epi_counts& c = e->last_counts;
+                if (c.susceptible != prev.susceptible || c.exposed != prev.exposed || c.infected != prev.infected ||
+                    c.hospitalized != prev.hospitalized || c.recovered != prev.recovered || c.deceased != prev.deceased)
+                    return engine_fail(e, EPI_ERR_STATE, "incrementally tracked Counts diverged from the recount at hour " + std::to_string(first_hour + k));
+            }
+            e->have_last_row = true;
+        } else e->last_counts.hour = first_hour + k;
+        const epi_counts& c = e->last_counts;
+        const uint64_t total = (uint64_t)c.susceptible + c.exposed + c.infected + c.hospitalized + c.recovered + c.deceased;
+        if (total != population[k])
+            return engine_fail(e, EPI_ERR_STATE, "counts total " + std::to_string(total) + " != population " + std::to_string(population[k]) + " at hour " + std::to_string(first_hour + k));
+        rows.push_back(c);
+    }
+    if (kind.back() == 2) e->have_last_row = false;
+    return EPI_OK;
+}
+
 // run hours [first, first+n) (n <= RING_ROWS), rows to out
 int run_chunk(epi_engine* e, uint32_t first_hour, uint32_t n, bool inject, epi_counts* out) {
+    if (!e->pend_kind.empty()) {
+        if (e->pend_kind.size() == 1 && e->pend_kind[0] == 2) { e->pend_kind.clear(); e->pend_population.clear(); }  // an exchange hour settled by epi_finish_hour
+        else return engine_fail(e, EPI_ERR_STATE, "hours are queued: call epi_collect_hours first");
+    }
     CU(cudaMemsetAsync(e->D.counts, 0, (size_t)n * 8 * sizeof(uint32_t), e->stream));
     int rc = ensure_epoch(e, first_hour, first_hour + n - 1);
     if (rc) return rc;
@@ -567,6 +695,8 @@ int epi_reset(epi_engine* e) {
     if (!e) return engine_fail(e, EPI_ERR_ARG, "null engine");
     CU(cudaSetDevice(e->device));
     const size_t nb = (size_t)e->P.n * sizeof(uint32_t);
+    e->pend_kind.clear();
+    e->pend_population.clear();
     CU(cudaMemcpyAsync(e->D.cell, e->i_cell, nb, cudaMemcpyDeviceToDevice, e->stream));
     CU(cudaMemcpyAsync(e->D.st, e->i_st, nb, cudaMemcpyDeviceToDevice, e->stream));
     CU(cudaMemcpyAsync(e->D.t0, e->i_t0, nb, cudaMemcpyDeviceToDevice, e->stream));
@@ -595,18 +725,42 @@ int epi_step(epi_engine* e, uint32_t hour, epi_counts* out) {
 int epi_enqueue_hour(epi_engine* e, uint32_t hour) {
     if (!e) return engine_fail(e, EPI_ERR_ARG, "null engine");
     CU(cudaSetDevice(e->device));
-    CU(cudaMemsetAsync(e->D.counts, 0, 8 * sizeof(uint32_t), e->stream));
-    int rc = ensure_epoch(e, hour, hour);
+    if (e->pend_kind.size() == 1 && e->pend_kind[0] == 2) { e->pend_kind.clear(); e->pend_population.clear(); }  // the previous exchange hour was settled by epi_finish_hour
+    return queue_hours(e, hour, 1, true);
+}
+
+int epi_enqueue_hours(epi_engine* e, uint32_t first_hour, uint32_t n_hours) {
+    if (!e) return engine_fail(e, EPI_ERR_ARG, "null engine");
+    CU(cudaSetDevice(e->device));
+    if (e->pend_kind.size() == 1 && e->pend_kind[0] == 2) { e->pend_kind.clear(); e->pend_population.clear(); }
+    return queue_hours(e, first_hour, n_hours, false);
+}
+
+int epi_collect_hours(epi_engine* e, epi_counts* rows_out, uint32_t max_rows, uint32_t* n_rows) {
+    if (!e || !n_rows || (!rows_out && max_rows)) return engine_fail(e, EPI_ERR_ARG, "null argument");
+    CU(cudaSetDevice(e->device));
+    *n_rows = 0;
+    std::vector<epi_counts> rows;
+    int rc = collect_hours(e, rows);
     if (rc) return rc;
-    {
-        Timed t(e, KK_MISC);
-        launch_set_clock(e->d_clock, Clock{hour, e->epoch_base, hour, 0}, e->stream);
+    if (rows.size() > max_rows) return engine_fail(e, EPI_ERR_ARG, "epi_collect_hours: rows_out too small");
+    for (const epi_counts& c : rows) {
+        rows_out[(*n_rows)++] = c;
+        rc = process_interventions(e, c, false);  // allocation_map.rs:306-337, as in epi_simulate_hours
+        if (rc) return rc;
     }
-    rc = enqueue_hour(e, hour, 0, false, false);
-    if (rc) return rc;
-    e->have_last_row = false;
-    CU(cudaGetLastError());
     return EPI_OK;
+}
+
+uint32_t epi_next_decision_hour(const epi_engine* e, uint32_t hour) {
+    if (!e) return hour;
+    // the next hour whose Counts the host must see before the following hour may run: start of day (lockdown.rs:55,
+    // hospital.rs:55,70), a configured vaccination hour (vaccination.rs:52), the unlock hour (lockdown.rs:69-73)
+    const epi::Interventions& iv = e->interventions;
+    uint32_t d = (hour + 23u) / 24u * 24u;
+    d = std::min(d, iv.vaccinate.next_hour(hour));
+    if (iv.lockdown.is_locked_down() && iv.lockdown.unlock_hour() >= hour) d = std::min(d, iv.lockdown.unlock_hour());
+    return d;
 }
 
 int epi_step_with_draws(epi_engine* e, uint32_t hour, const uint64_t* draws, epi_counts* out) {

@@ -38,6 +38,17 @@ struct epi_engine {
     cudaGraphExec_t day_graph = nullptr;
     uint32_t day_graph_launches = 0;
     bool graphs_enabled = true;
+    // hours queued by epi_enqueue_hours / epi_enqueue_hour whose Counts rows are still in the device ring (epi_collect_hours):
+    // ring row k = hour pend_first + k; pend_kind[k]: 0 row repeats the previous one (sleep hour without its own k_sleep),
+    // 1 row produced by the hour's kernels, 2 exchange hour (its row comes from epi_finish_hour)
+    uint32_t pend_first = 0;
+    std::vector<uint8_t> pend_kind;
+    std::vector<uint32_t> pend_population;  // live agents when the hour was queued (allocation_map.rs:128 check at collect time)
+    struct SegmentGraph {
+        cudaGraphExec_t exec = nullptr;
+        uint32_t launches = 0, n_sleep = 0, n_active = 0, n_scan = 0;
+    };
+    std::vector<std::pair<uint32_t, SegmentGraph>> segment_graphs;  // key = (first hour of day) * 32 + hours (1..24)
     // measurement
     bool timing = false;
     double kernel_ms[EPI_N_KERNEL_KINDS] = {0};

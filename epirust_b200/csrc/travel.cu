@@ -100,14 +100,34 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* w
 // Ordered compaction of the leaving candidates.  Pass 1 evaluates the flag of every slot once, keeps the warp ballots and
 // counts per block of 1024 slots; one block scans the counts; pass 2 places the flagged slots from the ballots (it reads
 // reg[] again only for the few flagged agents).
-constexpr uint32_t SEL_BLOCK = 1024;
-__global__ void __launch_bounds__(SEL_BLOCK) k_travel_flag_count(Params P, DevPtrs D, TravelArgs A, uint32_t* __restrict__ block_counts, uint32_t* __restrict__ ballots) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t f = i < P.n ? travel_flag(P, A, i, D.st[i], D.reg[i]) : 0u;
-    const unsigned b = __ballot_sync(0xFFFFFFFFu, f != 0);
-    if ((threadIdx.x & 31u) == 0) ballots[i >> 5] = b;
-    const int n = __syncthreads_count(f != 0);
-    if (threadIdx.x == 0) block_counts[blockIdx.x] = (uint32_t)n;
+constexpr uint32_t SEL_BLOCK = 1024;  // slots per count / offset entry
+// 256 threads x 4 consecutive slots (two 128-bit loads per thread); eight threads assemble one 32-slot ballot word
+__global__ void __launch_bounds__(256) k_travel_flag_count(Params P, DevPtrs D, TravelArgs A, uint32_t* __restrict__ block_counts, uint32_t* __restrict__ ballots) {
+    __shared__ uint32_t s_count;
+    if (threadIdx.x == 0) s_count = 0;
+    __syncthreads();
+    const uint32_t i0 = (blockIdx.x * 256u + threadIdx.x) * 4u;
+    uint32_t nib = 0;
+    if (i0 + 3u < P.n) {
+        const uint4 s4 = __ldcs(reinterpret_cast<const uint4*>(D.st + i0)), r4 = __ldcs(reinterpret_cast<const uint4*>(D.reg + i0));
+        nib = (travel_flag(P, A, i0, s4.x, r4.x) ? 1u : 0u) | (travel_flag(P, A, i0 + 1u, s4.y, r4.y) ? 2u : 0u) |
+              (travel_flag(P, A, i0 + 2u, s4.z, r4.z) ? 4u : 0u) | (travel_flag(P, A, i0 + 3u, s4.w, r4.w) ? 8u : 0u);
+    } else {
+#pragma unroll
+        for (uint32_t j = 0; j < 4; ++j)
+            if (i0 + j < P.n && travel_flag(P, A, i0 + j, D.st[i0 + j], D.reg[i0 + j])) nib |= 1u << j;
+    }
+    uint32_t w = nib << ((threadIdx.x & 7u) * 4u);
+    w |= __shfl_xor_sync(0xFFFFFFFFu, w, 1);
+    w |= __shfl_xor_sync(0xFFFFFFFFu, w, 2);
+    w |= __shfl_xor_sync(0xFFFFFFFFu, w, 4);
+    if ((threadIdx.x & 7u) == 0) ballots[i0 >> 5] = w;  // written for every group of the launch, also beyond P.n
+    uint32_t c = (threadIdx.x & 7u) == 0 ? (uint32_t)__popc(w) : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
+    if ((threadIdx.x & 31u) == 0 && c) atomicAdd(&s_count, c);
+    __syncthreads();
+    if (threadIdx.x == 0) block_counts[blockIdx.x] = s_count;
 }
 
 // exclusive scan of the block counts by ONE block (launched 3 times per simulated day)
@@ -128,18 +148,23 @@ __global__ void __launch_bounds__(1024) k_travel_scan(uint32_t* __restrict__ blo
     }
 }
 
-__global__ void __launch_bounds__(SEL_BLOCK) k_travel_scatter(Params P, DevPtrs D, TravelArgs A, TravelPtrs T, const uint32_t* __restrict__ block_offsets,
-                                                               const uint32_t* __restrict__ ballots) {
-    __shared__ uint32_t warp_sums[32];
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const unsigned b = ballots[i >> 5];  // written for every warp of the launch, also beyond P.n
-    uint32_t total;
-    const uint32_t before = block_exclusive_scan(lane == 0 ? (uint32_t)__popc(b) : 0u, warp_sums, &total);  // lane 0 holds the flagged slots in earlier warps
-    const uint32_t warp_base = __shfl_sync(0xFFFFFFFFu, before, 0);
-    (void)warp;
-    if ((b >> lane) & 1u) {
-        const uint32_t at = block_offsets[blockIdx.x] + warp_base + (uint32_t)__popc(b & ((1u << lane) - 1u));
+// one warp per block of 1024 slots: lane l owns ballot word l of the block
+__global__ void __launch_bounds__(256) k_travel_scatter(Params P, DevPtrs D, TravelArgs A, TravelPtrs T, const uint32_t* __restrict__ block_offsets,
+                                                         const uint32_t* __restrict__ ballots, uint32_t n_blocks) {
+    const uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const unsigned lane = threadIdx.x & 31u;
+    if (g >= n_blocks) return;
+    uint32_t b = ballots[g * 32u + lane];
+    uint32_t incl = (uint32_t)__popc(b);
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if ((int)lane >= o) incl += y;
+    }
+    uint32_t at = block_offsets[g] + incl - (uint32_t)__popc(b);
+    while (b) {
+        const uint32_t i = (g * 32u + lane) * 32u + (uint32_t)__ffs((int)b) - 1u;
+        b &= b - 1u;
         if (at < T.list_cap) {
             T.list_slot[at] = i;
             uint32_t dest = 0;
@@ -149,6 +174,7 @@ __global__ void __launch_bounds__(SEL_BLOCK) k_travel_scatter(Params P, DevPtrs 
             }
             T.list_dest[at] = dest;
         } else atomicOr(&T.tv->err, TERR_LIST_OVERFLOW);
+        ++at;
     }
 }
 
@@ -539,9 +565,9 @@ unsigned launch_travel_leave(const Params& P, const DevPtrs& D, const TravelArgs
                              uint32_t stride, cudaStream_t s) {
     const unsigned nb = (P.n + SEL_BLOCK - 1u) / SEL_BLOCK;
     uint32_t* ballots = block_counts + nb + 1;  // the host allocates both in one array
-    k_travel_flag_count<<<nb, SEL_BLOCK, 0, s>>>(P, D, A, block_counts, ballots);
+    k_travel_flag_count<<<nb, 256, 0, s>>>(P, D, A, block_counts, ballots);
     k_travel_scan<<<1, 1024, 0, s>>>(block_counts, nb, T.tv);
-    k_travel_scatter<<<nb, SEL_BLOCK, 0, s>>>(P, D, A, T, block_counts, ballots);
+    k_travel_scatter<<<(nb + 7u) / 8u, 256, 0, s>>>(P, D, A, T, block_counts, ballots, nb);
     k_travel_plan<<<1, 1024, 0, s>>>(P, A, T, send, stride);
     unsigned launches = 6;
     if (A.kind == TRAVEL_COMMUTE) { k_travel_rank<<<(unsigned)T.n_regions, 1024, 0, s>>>(T); ++launches; }

@@ -181,6 +181,20 @@ class Engine:
         """CitizenLocationMap::simulate for one hour, asynchronously (no Counts row; see epi_finish_hour)."""
         self._check(self.L.epi_enqueue_hour(self.h, hour))
 
+    def enqueue_hours(self, first_hour, n_hours):
+        """Queue hours [first_hour, first_hour + n_hours) without waiting (epi_enqueue_hours); rows come from collect_hours()."""
+        self._check(self.L.epi_enqueue_hours(self.h, first_hour, n_hours))
+
+    def collect_hours(self, max_rows=2400):
+        """Wait for the queued hours; their Counts rows [n, 7] in order (an exchange hour's row comes from finish_hour)."""
+        rows = np.zeros((max_rows, 7), np.uint32)
+        n = C.c_uint32(0)
+        self._check(self.L.epi_collect_hours(self.h, _ptr(rows), max_rows, C.byref(n)))
+        return rows[: n.value]
+
+    def next_decision_hour(self, hour):
+        return int(self.L.epi_next_decision_hour(self.h, hour))
+
     def sync(self):
         self._check(self.L.epi_sync(self.h))
 

@@ -115,23 +115,32 @@ class MultiRegion:
             e.travel_unpack(hour, kind, recv.data_ptr(), self.stride, want_counts=not deferred)
 
     def run(self, first_hour, n_hours, rows_out=None):
-        """Hours first_hour .. first_hour + n_hours - 1 of every local region.  Returns rows[n_local, n_hours, 7]."""
+        """Hours first_hour .. first_hour + n_hours - 1 of every local region.  Returns rows[n_local, n_hours, 7].
+
+        The host waits for the device only where it has to look at Counts: after an exchange hour (epi_finish_hour) and at a
+        decision hour of process_interventions (start of day, vaccination hour, unlock hour).  Everything in between -- the
+        plain hours before an exchange, the exchange hour's kernels, pack, collective and unpack -- is queued back to back."""
         rows = rows_out if rows_out is not None else np.zeros((len(self.engines), n_hours, 7), np.uint32)
         hour, last = first_hour, first_hour + n_hours - 1
         while hour <= last:
             x = self.next_exchange_hour(hour, last)
-            stop = x if x is not None else last + 1
-            if stop > hour:
-                for i, e in enumerate(self.engines):
-                    got, _ = e.simulate_hours(hour, stop - hour, stop_rule=False, out=rows[i, hour - first_hour:stop - first_hour])
-            if x is None:
-                break
-            for e in self.engines:
-                e.enqueue_hour(x)
-            self._do_exchange(x, exchange_kind(self.plan, self.kinds, x))
+            decision = min(e.next_decision_hour(hour) for e in self.engines)
+            seg_end = min(last, decision, (x - 1) if x is not None else last)  # last plain hour queued in this round
+            if seg_end >= hour:
+                for e in self.engines:
+                    e.enqueue_hours(hour, seg_end - hour + 1)
+            exchange_now = x is not None and x == seg_end + 1 and not (seg_end >= hour and seg_end == decision)
+            if exchange_now:
+                for e in self.engines:
+                    e.enqueue_hour(x)
+                self._do_exchange(x, exchange_kind(self.plan, self.kinds, x))
             for i, e in enumerate(self.engines):
-                rows[i, x - first_hour] = e.finish_hour(x)
-            hour = x + 1
+                got = e.collect_hours()
+                if len(got):
+                    rows[i, hour - first_hour:hour - first_hour + len(got)] = got
+                if exchange_now:
+                    rows[i, x - first_hour] = e.finish_hour(x)
+            hour = (x if exchange_now else seg_end) + 1
         return rows
 
     def active_cases_everywhere(self, last_rows):

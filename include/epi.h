@@ -136,6 +136,17 @@ int epi_step(epi_engine* e, uint32_t hour, epi_counts* out);
 /* epi_step without waiting for the hour to finish and without its Counts row: the multi-region loop enqueues the exchange hour,
  * packs the leavers behind it on the same stream and reads the row from epi_finish_hour. */
 int epi_enqueue_hour(epi_engine* e, uint32_t hour);
+/* A multi-region day without intermediate host waits.  epi_enqueue_hours queues the hours [first_hour, first_hour + n_hours)
+ * -- consecutive with what is already queued, none of them an exchange hour -- and returns at once (replaying a CUDA graph
+ * per (hour of day, n_hours)); their Counts rows stay on the device.  epi_collect_hours waits for everything queued
+ * (including an exchange hour queued by epi_enqueue_hour and its pack / unpack), returns the rows of the non-exchange hours
+ * in order and runs process_interventions on each, like epi_simulate_hours; the exchange hour's own row then comes from
+ * epi_finish_hour.  A queued segment must end at epi_next_decision_hour() at the latest: the next hour >= `hour` whose
+ * Counts the host has to see before the following hour may run (start of day: lockdown.rs:55, hospital.rs:55,70; a
+ * configured vaccination hour: vaccination.rs:52; the unlock hour: lockdown.rs:69-73). */
+int epi_enqueue_hours(epi_engine* e, uint32_t first_hour, uint32_t n_hours);
+int epi_collect_hours(epi_engine* e, epi_counts* rows_out, uint32_t max_rows, uint32_t* n_rows);
+uint32_t epi_next_decision_hour(const epi_engine* e, uint32_t hour);
 /* Same hour with every random draw injected: draws[agent * EPI_DRAWS_PER_AGENT + slot] (host memory).
  * This is the bit-exact sub-step test entry (no reference equivalent; the reference cannot inject draws). */
 int epi_step_with_draws(epi_engine* e, uint32_t hour, const uint64_t* draws, epi_counts* out);

@@ -23,3 +23,16 @@ for e in day:
     elif e['k'] == 'k_commit': out.append(cur + ' | commit %3.0fus %4.0fMB' % (t, mb)); k += 1
     else: out.append('%s %.0fus %.0fMB' % (e['k'], t, mb))
 print('day total %.0f us' % tot); print('\n'.join(out))
+# --json FILE: DRAM bytes of the average active-hour pass of that day (all 18 k_hour + 18 k_commit launches), for bench.py's roofline.traffic
+if '--json' in sys.argv:
+    import json
+    kh = [e for e in day if e['k'].startswith('k_hour')]; kc = [e for e in day if e['k'] == 'k_commit']
+    byt = lambda e: e.get('dram__bytes_read.sum', 0) + e.get('dram__bytes_write.sum', 0)
+    unit = 1.0
+    j = {'k_hour': {'dram_bytes_per_launch': sum(map(byt, kh)) * unit / len(kh), 'launches_captured': len(kh)},
+         'k_commit': {'dram_bytes_per_launch': sum(map(byt, kc)) * unit / len(kc), 'launches_captured': len(kc)},
+         'workload': '10m',
+         'source': 'ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none on bench.py --steps 2 --warmup 3: every k_hour / k_commit launch of one simulated day (day 3), B200; profiles/*_launches_10m.csv'}
+    j['pass_dram_bytes_per_launch'] = j['k_hour']['dram_bytes_per_launch'] + j['k_commit']['dram_bytes_per_launch']
+    json.dump(j, open(sys.argv[sys.argv.index('--json') + 1], 'w'), indent=1)
+

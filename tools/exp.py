@@ -1,8 +1,8 @@
 """Build kernel-experiment variants of the library: exp/lib_<name>.so = kernels.cu compiled with extra -D flags.
-    python tools_exp.py base: plainoff:-DEPI_EXP=1 minb8:-DEPI_MINB=8
-(then on the GPU box: EPI_LIB=$PWD/exp/lib_<name>.so python bench.py ...; scripts_gpu_exp.sh loops over $VARIANTS)"""
+    python tools/exp.py base: plainoff:-DEPI_EXP=1 minb8:-DEPI_MINB=8
+(then on the GPU box: EPI_LIB=$PWD/exp/lib_<name>.so python bench.py ...; tools/gpu_ab.sh runs the A/B)"""
 import os, subprocess, sys
-ROOT = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from epirust_b200 import build as B
 B.build()
