@@ -230,12 +230,13 @@ __global__ void __launch_bounds__(256) k_hospital_scan(Params P, const uint8_t* 
     }
 }
 
-// PLAIN: an hour of day at which perform_movements has no special case for anybody but hospital staff (h = 9..11, 13..15,
-// 18..22: everybody who can move walks inside current_area) -- 11 of the 16 movement hours.  The kernel is issue-bound,
-// so the goto / area-change logic is compiled out for them (h is then a dummy).
-template <int KIND, bool INJECT, bool PLAIN = false>
-__global__ void __launch_bounds__(256, KIND == KIND_MOVE ? EPI_MINB : 4) k_hour(Params P, DevPtrs D, uint32_t hour_offset, uint32_t h_arg) {
-    const uint32_t h = PLAIN ? 9u : h_arg;
+// HOD: the hour of day the movement kernel is compiled for.  perform_movements (citizen/mod.rs:257-349) has special cases at
+// h = 7, 8, 12, 16, 17 only; each of them and "any other hour" (HOD = 9: everybody who can move walks inside current_area,
+// 11 of the 16 movement hours) gets its own instantiation, so the goto / area-change logic of the other hours is compiled
+// out (the kernel is issue-and-latency bound: -10 % time on the plain hours against one kernel with a run-time hour).
+template <int KIND, bool INJECT, uint32_t HOD = 0>
+__global__ void __launch_bounds__(256, KIND == KIND_MOVE ? EPI_MINB : 4) k_hour(Params P, DevPtrs D, uint32_t hour_offset) {
+    constexpr uint32_t h = HOD;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n) return;
     if ((threadIdx.x & 7u) == 0 && i + PREFETCH_AHEAD < P.n) {  // one prefetch per 32-byte sector
@@ -611,21 +612,19 @@ void launch_hospital_scan(const Params& P, const DevPtrs& D, cudaStream_t s) {
     if (blocks == 0) blocks = 1;
     k_hospital_scan<<<blocks, 256, 0, s>>>(P, D.grid, D.hosp_first);
 }
-// citizen/mod.rs:257-349: the hours of day perform_movements treats specially are 7, 8, 12, 16, 17
-static inline bool hour_is_plain(uint32_t h) {
-#if defined(EPI_EXP) && (EPI_EXP & 1)
-    return false;
-#else
-    return h >= 9 && h <= 22 && h != 12 && h != 16 && h != 17;
-#endif
-}
 template <bool INJECT>
 static void launch_hour_t(const Params& P, const DevPtrs& D, uint32_t hour_of_day, uint32_t hour_offset, cudaStream_t s) {
     const unsigned b = blocks_for(P.n);
-    if (hour_of_day == 0) k_hour<KIND_START, INJECT><<<b, 256, 0, s>>>(P, D, hour_offset, hour_of_day);
-    else if (hour_of_day == 23) k_hour<KIND_END, INJECT><<<b, 256, 0, s>>>(P, D, hour_offset, hour_of_day);
-    else if (hour_is_plain(hour_of_day)) k_hour<KIND_MOVE, INJECT, true><<<b, 256, 0, s>>>(P, D, hour_offset, hour_of_day);
-    else k_hour<KIND_MOVE, INJECT><<<b, 256, 0, s>>>(P, D, hour_offset, hour_of_day);
+    switch (hour_of_day) {
+        case 0: k_hour<KIND_START, INJECT><<<b, 256, 0, s>>>(P, D, hour_offset); break;
+        case 23: k_hour<KIND_END, INJECT><<<b, 256, 0, s>>>(P, D, hour_offset); break;
+        case 7: k_hour<KIND_MOVE, INJECT, 7><<<b, 256, 0, s>>>(P, D, hour_offset); break;
+        case 8: k_hour<KIND_MOVE, INJECT, 8><<<b, 256, 0, s>>>(P, D, hour_offset); break;
+        case 12: k_hour<KIND_MOVE, INJECT, 12><<<b, 256, 0, s>>>(P, D, hour_offset); break;
+        case 16: k_hour<KIND_MOVE, INJECT, 16><<<b, 256, 0, s>>>(P, D, hour_offset); break;
+        case 17: k_hour<KIND_MOVE, INJECT, 17><<<b, 256, 0, s>>>(P, D, hour_offset); break;
+        default: k_hour<KIND_MOVE, INJECT, 9><<<b, 256, 0, s>>>(P, D, hour_offset); break;  // 9..11, 13..15, 18..22 (1..6 are k_sleep's)
+    }
 }
 void launch_hour(const Params& P, const DevPtrs& D, uint32_t hour_of_day, uint32_t hour_offset, bool inject, cudaStream_t s) {
     if (inject) launch_hour_t<true>(P, D, hour_of_day, hour_offset, s);
