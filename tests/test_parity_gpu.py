@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 import oracle_ffi as O
-from epirust_b200.engine import Engine, make_config, run_standalone, STATE_FIELDS
+from epirust_b200.engine import Engine, EpiError, make_config, run_standalone, STATE_FIELDS
 
 pytestmark = pytest.mark.gpu
 
@@ -117,6 +117,38 @@ def test_run_hours_graph_path_equals_single_steps():
         rows2 = a.run_hours(24 * 6 + 6, 60)
         for i, hour in enumerate(range(24 * 6 + 6, 24 * 6 + 66)):
             assert (rows2[i] == b.step(hour)).all(), f"hour {hour}"
+
+
+def test_queued_hours_equal_simulate_hours():
+    """epi_enqueue_hours / epi_collect_hours (the no-wait path of the multi-region day) against epi_simulate_hours: same
+    Counts rows, same intervention events, same final state -- segments of odd lengths cut at epi_next_decision_hour."""
+    kw = dict(n_agents=10000, grid_size=250, hours=400, exposed=100, lockdown=(60, 0.1), hospital=20, vaccinate=((100, 0.2), (131, 0.1)))
+    gc = make_config(**kw)
+    with Engine(gc, seed=8) as a, Engine(gc, seed=8) as b:
+        want, _ = a.simulate_hours(1, 330)
+        got, hour, lengths = [], 1, [5, 1, 9, 24, 3, 17, 2, 30]
+        k = 0
+        while hour <= 330:
+            seg_end = min(330, b.next_decision_hour(hour), hour + lengths[k % len(lengths)] - 1)
+            b.enqueue_hours(hour, seg_end - hour + 1)
+            if seg_end != b.next_decision_hour(hour) and seg_end < 330 and k % 3 == 0:  # two segments behind one wait
+                nxt = min(330, b.next_decision_hour(seg_end + 1), seg_end + 4)
+                b.enqueue_hours(seg_end + 1, nxt - seg_end)
+                seg_end = nxt
+            rows = b.collect_hours()
+            assert rows[:, 0].tolist() == list(range(hour, seg_end + 1))
+            got.append(rows)
+            hour, k = seg_end + 1, k + 1
+        got = np.concatenate(got)
+        assert got.shape == want.shape and (got == want).all(), f"first differing hour {np.nonzero((got != want).any(axis=1))[0][:3] + 1}"
+        assert (a.intervention_events() == b.intervention_events()).all() and len(a.intervention_events()) >= 3
+        sa, sb = a.get_state(), b.get_state()
+        for f in STATE_FIELDS:
+            assert (sa[f] == sb[f]).all()
+        with pytest.raises(EpiError, match="queued"):  # a plain run may not overtake queued hours
+            b.enqueue_hours(331, 2)
+            b.run_hours(340, 1)
+        b.collect_hours()
 
 
 def test_whole_run_with_interventions_matches_oracle(tmp_path):
