@@ -39,6 +39,9 @@
 
 namespace epi {
 
+#ifndef EPI_HBS
+#define EPI_HBS 128  // threads per CTA of k_hour: 12 CTAs / SM (32: 0.215 ms, 64: 0.193, 128: 0.189, 256: 0.190, 512: 0.247 per launch at 10 M agents)
+#endif
 #ifndef EPI_MINB
 #define EPI_MINB 6  // resident CTAs per SM the movement-hour kernel is compiled for (40 registers; 8 -> 32 registers + spills, measured slower)
 #endif
@@ -235,7 +238,7 @@ __global__ void __launch_bounds__(256) k_hospital_scan(Params P, const uint8_t* 
 // 11 of the 16 movement hours) gets its own instantiation, so the goto / area-change logic of the other hours is compiled
 // out (the kernel is issue-and-latency bound: -10 % time on the plain hours against one kernel with a run-time hour).
 template <int KIND, bool INJECT, uint32_t HOD = 0>
-__global__ void __launch_bounds__(256, KIND == KIND_MOVE ? EPI_MINB : 4) k_hour(Params P, DevPtrs D, uint32_t hour_offset) {
+__global__ void __launch_bounds__(EPI_HBS, KIND == KIND_MOVE ? EPI_MINB * (256 / EPI_HBS) : 4 * (256 / EPI_HBS)) k_hour(Params P, DevPtrs D, uint32_t hour_offset) {
     constexpr uint32_t h = HOD;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n) return;
@@ -614,16 +617,16 @@ void launch_hospital_scan(const Params& P, const DevPtrs& D, cudaStream_t s) {
 }
 template <bool INJECT>
 static void launch_hour_t(const Params& P, const DevPtrs& D, uint32_t hour_of_day, uint32_t hour_offset, cudaStream_t s) {
-    const unsigned b = blocks_for(P.n);
+    const unsigned b = (P.n + EPI_HBS - 1u) / EPI_HBS;
     switch (hour_of_day) {
-        case 0: k_hour<KIND_START, INJECT><<<b, 256, 0, s>>>(P, D, hour_offset); break;
-        case 23: k_hour<KIND_END, INJECT><<<b, 256, 0, s>>>(P, D, hour_offset); break;
-        case 7: k_hour<KIND_MOVE, INJECT, 7><<<b, 256, 0, s>>>(P, D, hour_offset); break;
-        case 8: k_hour<KIND_MOVE, INJECT, 8><<<b, 256, 0, s>>>(P, D, hour_offset); break;
-        case 12: k_hour<KIND_MOVE, INJECT, 12><<<b, 256, 0, s>>>(P, D, hour_offset); break;
-        case 16: k_hour<KIND_MOVE, INJECT, 16><<<b, 256, 0, s>>>(P, D, hour_offset); break;
-        case 17: k_hour<KIND_MOVE, INJECT, 17><<<b, 256, 0, s>>>(P, D, hour_offset); break;
-        default: k_hour<KIND_MOVE, INJECT, 9><<<b, 256, 0, s>>>(P, D, hour_offset); break;  // 9..11, 13..15, 18..22 (1..6 are k_sleep's)
+        case 0: k_hour<KIND_START, INJECT><<<b, EPI_HBS, 0, s>>>(P, D, hour_offset); break;
+        case 23: k_hour<KIND_END, INJECT><<<b, EPI_HBS, 0, s>>>(P, D, hour_offset); break;
+        case 7: k_hour<KIND_MOVE, INJECT, 7><<<b, EPI_HBS, 0, s>>>(P, D, hour_offset); break;
+        case 8: k_hour<KIND_MOVE, INJECT, 8><<<b, EPI_HBS, 0, s>>>(P, D, hour_offset); break;
+        case 12: k_hour<KIND_MOVE, INJECT, 12><<<b, EPI_HBS, 0, s>>>(P, D, hour_offset); break;
+        case 16: k_hour<KIND_MOVE, INJECT, 16><<<b, EPI_HBS, 0, s>>>(P, D, hour_offset); break;
+        case 17: k_hour<KIND_MOVE, INJECT, 17><<<b, EPI_HBS, 0, s>>>(P, D, hour_offset); break;
+        default: k_hour<KIND_MOVE, INJECT, 9><<<b, EPI_HBS, 0, s>>>(P, D, hour_offset); break;  // 9..11, 13..15, 18..22 (1..6 are k_sleep's)
     }
 }
 void launch_hour(const Params& P, const DevPtrs& D, uint32_t hour_of_day, uint32_t hour_offset, bool inject, cudaStream_t s) {
