@@ -523,19 +523,57 @@ __global__ void __launch_bounds__(256) k_commit(Params P, DevPtrs D, uint32_t ho
     }
 }
 
+// Four agents per thread (one 128-bit load); the six Counts columns travel as 10-bit fields of one 64-bit word through the warp
+// reduction (a warp holds at most 128 agents), so the whole recount costs ten shuffles and six shared atomics per warp.
 __global__ void __launch_bounds__(256) k_sleep(Params P, DevPtrs D, uint32_t hour_offset) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ uint32_t s_cnt[6];
+    if (threadIdx.x < 6) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4u;
     const uint32_t hour = D.clock->hour_base + hour_offset;
-    uint32_t cat = 6;
-    if (i < P.n) {
-        uint32_t s = D.st[i];
-        if ((s & ST_STATE_MASK) != ST_ABSENT && ((s >> ST_WS_SHIFT) & 3u) != WS_STAFF && (s & ST_AREA_MASK) != (AK_HOME << ST_AREA_SHIFT)) {
-            s = (s & ~ST_AREA_MASK) | (AK_HOME << ST_AREA_SHIFT);
-            D.st[i] = s;
-        }
-        cat = count_category(s);
+    uint32_t st[4] = {ST_ABSENT, ST_ABSENT, ST_ABSENT, ST_ABSENT};
+    const bool full = i0 + 3u < P.n;
+    if (full) {
+        const uint4 v = *reinterpret_cast<const uint4*>(D.st + i0);
+        st[0] = v.x; st[1] = v.y; st[2] = v.z; st[3] = v.w;
+    } else {
+#pragma unroll
+        for (uint32_t j = 0; j < 4; ++j)
+            if (i0 + j < P.n) st[j] = D.st[i0 + j];
     }
-    block_count(cat, D.counts + (size_t)(hour - D.clock->ring_base) * 8);
+    unsigned long long packed = 0;
+    bool changed = false;
+#pragma unroll
+    for (uint32_t j = 0; j < 4; ++j) {
+        uint32_t s = st[j];
+        if ((s & ST_STATE_MASK) != ST_ABSENT && ((s >> ST_WS_SHIFT) & 3u) != WS_STAFF && (s & ST_AREA_MASK) != (AK_HOME << ST_AREA_SHIFT)) {
+            s = (s & ~ST_AREA_MASK) | (AK_HOME << ST_AREA_SHIFT);  // citizen/mod.rs:244-248
+            st[j] = s;
+            changed = true;
+        }
+        const uint32_t cat = count_category(s);
+        if (cat < 6u) packed += 1ull << (10u * cat);
+    }
+    if (changed) {
+        if (full) *reinterpret_cast<uint4*>(D.st + i0) = make_uint4(st[0], st[1], st[2], st[3]);
+        else {
+#pragma unroll
+            for (uint32_t j = 0; j < 4; ++j)
+                if (i0 + j < P.n) D.st[i0 + j] = st[j];
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) packed += __shfl_xor_sync(0xFFFFFFFFu, packed, o);
+    if ((threadIdx.x & 31u) == 0) {
+#pragma unroll
+        for (uint32_t c = 0; c < 6; ++c) {
+            const uint32_t v = (uint32_t)(packed >> (10u * c)) & 1023u;
+            if (v) atomicAdd(&s_cnt[c], v);
+        }
+    }
+    __syncthreads();
+    uint32_t* out_row = D.counts + (size_t)(hour - D.clock->ring_base) * 8;
+    if (threadIdx.x < 6 && s_cnt[threadIdx.x]) atomicAdd(&out_row[threadIdx.x], s_cnt[threadIdx.x]);
 }
 
 __global__ void k_set_clock(Clock* clock, Clock value) { *clock = value; }
@@ -636,7 +674,7 @@ void launch_hour(const Params& P, const DevPtrs& D, uint32_t hour_of_day, uint32
 void launch_recount(const Params& P, const DevPtrs& D, cudaStream_t s) { k_recount<<<blocks_for(P.n), 256, 0, s>>>(P, D.st, D.tot); }
 void launch_set_clock(Clock* clock, const Clock& value, cudaStream_t s) { k_set_clock<<<1, 1, 0, s>>>(clock, value); }
 void launch_commit(const Params& P, const DevPtrs& D, uint32_t hour_offset, cudaStream_t s) { k_commit<<<blocks_for((P.n + 3u) / 4u), 256, 0, s>>>(P, D, hour_offset); }
-void launch_sleep(const Params& P, const DevPtrs& D, uint32_t hour_offset, cudaStream_t s) { k_sleep<<<blocks_for(P.n), 256, 0, s>>>(P, D, hour_offset); }
+void launch_sleep(const Params& P, const DevPtrs& D, uint32_t hour_offset, cudaStream_t s) { k_sleep<<<blocks_for((P.n + 3u) / 4u), 256, 0, s>>>(P, D, hour_offset); }
 void launch_lock(const Params& P, const DevPtrs& D, cudaStream_t s) { k_lock<<<blocks_for(P.n), 256, 0, s>>>(P, D.st); }
 void launch_unlock(const Params& P, const DevPtrs& D, cudaStream_t s) { k_unlock<<<blocks_for(P.n), 256, 0, s>>>(P, D.st); }
 void launch_vaccinate(const Params& P, const DevPtrs& D, uint64_t thr, uint32_t hour, cudaStream_t s) { k_vaccinate<<<blocks_for(P.n), 256, 0, s>>>(P, D.st, thr, hour); }
