@@ -43,6 +43,27 @@ def test_mean_std_recipe_truncates_to_the_shortest_run():
     assert E.peak_infected(a) == (1.0, 3.0)
 
 
+def test_post_processing_recipes_of_the_reference_plot_scripts(tmp_path):
+    # engine/plot/collate_all_simulations.py (EpiCurves.to_csv), update_total_infections.py, merge_regions_data.py
+    a = np.array([[1, 10, 0, 0, 0, 0, 0], [2, 9, 1, 0, 0, 0, 0], [3, 8, 1, 1, 0, 0, 0]])
+    b = np.array([[1, 10, 0, 0, 0, 0, 0], [2, 7, 3, 0, 0, 0, 0]])
+    out = tmp_path / "collated_simulation.csv"
+    E.collate_to_csv([a, b], out)
+    lines = out.read_text().splitlines()
+    assert lines[0] == "susceptible,susceptible_std,exposed,exposed_std,infected,infected_std,hospitalized,hospitalized_std,recovered,recovered_std,deceased,deceased_std,hour"
+    row2 = [float(v) for v in lines[2].split(",")]
+    assert row2[:4] == [8.0, 1.0, 2.0, 1.0] and row2[-1] == 2 and len(lines) == 3  # population std (numpy .std()), shortest run
+    rows = np.array([[h, 0, 0, i, hsp, r, d] for h, (i, hsp, r, d) in enumerate([(1, 0, 0, 0), (3, 1, 0, 0), (2, 1, 2, 1), (0, 0, 5, 2)], 1)])
+    t = E.with_total_infected(rows, ma_window=2)
+    assert t["totalinfected"].tolist() == [1, 4, 6, 7]
+    assert np.isnan(t["ma_infected"][0]) and t["ma_infected"][1:].tolist() == [2.0, 2.5, 1.0] and t["ma_deceased"][3] == 1.5
+    m = E.merge_regions([a, b])
+    assert m[:, 1].tolist() == [20, 16, 8] and m[:, 0].tolist() == [2, 4, 3]  # the script sums the hour column too
+    p = tmp_path / "simulation_0_x.csv"
+    p.write_text("hour,susceptible,exposed,infected,hospitalized,recovered,deceased\n1,10,0,0,0,0,0\n2,9,1,0,0,0,0\n")
+    assert E.read_rows(p).tolist() == [[1, 10, 0, 0, 0, 0, 0], [2, 9, 1, 0, 0, 0, 0]]
+
+
 def test_compare_flags_a_shifted_ensemble():
     rng = np.random.default_rng(0)
     base = np.zeros((20, 50, 7))
