@@ -1,12 +1,14 @@
 // sm_100a kernels of the per-hour agent step.  HBM/L2-bound integer work: no tensor cores.
 //
 //   k_hospital_scan   first vacant hospital cell in row-major order        (allocation_map.rs:144-147)
-//   k_hour<KIND>      one agent per thread: routine, movement proposal against the start-of-hour grid, disease
+//   k_hour<KIND, HOD> one agent per thread: routine, movement proposal against the start-of-hour grid, disease
 //                     transition, Counts; atomicMax claim on the target cell (citizen/mod.rs:227-432,
 //                     default_disease_handler.rs:31-103, counts.rs:126-140).  KIND: the hour-of-day class
-//                     (ROUTINE_START_TIME, ROUTINE_END_TIME, else perform_movements) -- uniform per launch.
-//   k_commit          lowest-id claimant moves, loser stays; grid bytes updated in place (allocation_map.rs:93-102,131-134)
-//   k_sleep           hours 1..6: current_area := home (citizen/mod.rs:244-248) + Counts recount
+//                     (ROUTINE_START_TIME, ROUTINE_END_TIME, else perform_movements); HOD: the movement hour the kernel is
+//                     compiled for (7, 8, 12, 16, 17 or "any other") -- both uniform per launch.
+//   k_commit          four agents per thread: lowest-id claimant moves, loser stays; grid bytes updated in place
+//                     (allocation_map.rs:93-102,131-134)
+//   k_sleep           hours 1..6, four agents per thread: current_area := home (citizen/mod.rs:244-248) + Counts recount
 //   k_lock / k_unlock / k_vaccinate   intervention sweeps (allocation_map.rs:349-387)
 //
 // Synchronous-update argument (why the grid can be updated in place): every proposal targets a cell that was vacant
@@ -65,7 +67,7 @@ __device__ __forceinline__ uint32_t ld_early_rw(const uint32_t* p) {  // for arr
 // agents): the first of the two dependent memory round trips of an agent-hour then costs an L2 hit instead of a DRAM access
 // (+5 % agent-steps/s at 10 M agents; half a wave is as good, 2 and 4 waves are worse; prefetching the grid rows of the agent
 // ahead as well costs more issue slots than it saves).
-constexpr uint32_t PREFETCH_AHEAD = 148u * 6u * 256u;  // one wave at 6 CTAs / SM
+constexpr uint32_t PREFETCH_AHEAD = 148u * 6u * 256u;  // one wave of k_hour: 148 SMs x 48 warps
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void st_stream(uint32_t* p, uint32_t v) { asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
