@@ -312,10 +312,14 @@ def run_ours(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, threads, sample, _, _ = cpu_reference(args.workload if args.workload in ("1m", "2m") else "1m", 3, 1, budget_s=25.0)
+        cpu_wl = args.workload if args.workload in ("1m", "2m") else "1m"
+        v, threads, sample, _, _ = cpu_reference(cpu_wl, 3, 1, budget_s=25.0)
         if args.workload not in ("1m", "2m"):
             sample = "SUB-SAMPLE at the same density rho=0.16: " + sample
         cpu = {"value": v, "unit": "agent-steps/s", "cores": threads, "kind": "port", "sample": sample}
+        if threads > 4:  # the reference's default thread count (engine-app/src/main.rs:80 `-t 4`), SURVEY.md section 8d
+            v4, _, _, _, _ = cpu_reference(cpu_wl, 2, 1, budget_s=15.0, threads=4)
+            cpu["at_reference_default_threads"] = {"value": v4, "cores": 4}
 
     if rank == 0:
         wl = WORKLOAD_NAMES[args.workload]
