@@ -1,3 +1,6 @@
+        e2e = {"value": world * n * 24.0 * K / (wall_ms_max * 1e-3), "unit": "agent-steps/s", "h2d_bytes_per_step": 0,
+               "d2h_bytes_per_step": 24 * 28 + 3 * (4 * (8 + world) + 4 * 32 * 8),
+               "note": "host wall clock around the timed K days (max over ranks) through the public multi-region API (epirust_b200.multi.MultiRegion.run); the state stays in HBM (a region has no per-day host input), per day the 24 Counts rows come back and, per exchange, the exchange's scalars (TravelVars) and the running Counts totals; traveller records go GPU to GPU"}
 #!/usr/bin/env python
 """bench.py -- agent-steps/s of the per-hour agent step on B200 (BASELINE.json metric).
 
