@@ -1,6 +1,3 @@
-        e2e = {"value": world * n * 24.0 * K / (wall_ms_max * 1e-3), "unit": "agent-steps/s", "h2d_bytes_per_step": 0,
-               "d2h_bytes_per_step": 24 * 28 + 3 * (4 * (8 + world) + 4 * 32 * 8),
-               "note": "host wall clock around the timed K days (max over ranks) through the public multi-region API (epirust_b200.multi.MultiRegion.run); the state stays in HBM (a region has no per-day host input), per day the 24 Counts rows come back and, per exchange, the exchange's scalars (TravelVars) and the running Counts totals; traveller records go GPU to GPU"}
 #!/usr/bin/env python
 """bench.py -- agent-steps/s of the per-hour agent step on B200 (BASELINE.json metric).
 
@@ -306,11 +303,10 @@ def run_ours(args):
         e2e = {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": 24 * 28,
                "note": "population uploaded from pinned host arrays once (amortised over the K days), 24 Counts rows read back per day"}
     else:
-        # the same K days by the host's wall clock through the public multi-region API (epirust_b200.multi.MultiRegion.run):
-        # Counts rows come back to the host every segment, the exchange's count / index lists cross PCIe both ways
-        e2e = {"value": world * n * 24.0 * K / (wall_ms_max * 1e-3), "unit": "agent-steps/s", "h2d_bytes_per_step": 3 * 4 * 3 * (n // 2000) * (world - 1),
-               "d2h_bytes_per_step": 24 * 28 + 3 * 8 * (n // 2000) * (world - 1),
-               "note": "host wall clock around the timed K days (max over ranks); per day 24 Counts rows D2H plus, per exchange, the leavers' slot / destination lists D2H and the arrivals' slot / house / office lists H2D (estimated from the travel plan)"}
+        # the same K days by the host's wall clock through the public multi-region API (epirust_b200.multi.MultiRegion.run)
+        e2e = {"value": world * n * 24.0 * K / (wall_ms_max * 1e-3), "unit": "agent-steps/s", "h2d_bytes_per_step": 0,
+               "d2h_bytes_per_step": 24 * 28 + 3 * (4 * (8 + world) + 4 * 32 * 8),
+               "note": "host wall clock around the timed K days (max over ranks); the state stays in HBM (a region has no per-day host input), per day the 24 Counts rows come back and, per exchange, the exchange's scalars (TravelVars) and the running Counts totals; traveller records go GPU to GPU"}
     eng.close()
 
     cpu = None
