@@ -141,14 +141,20 @@ int enqueue_hour(epi_engine* e, uint32_t hour, uint32_t hour_offset, bool inject
     return EPI_OK;
 }
 
-// claim stamps: stamp = hour - epoch_base + 1 must stay below 2^(32 - id_bits)
+// claim stamps: stamp = hour - epoch_base + 1 must stay below 2^(32 - id_bits) (k_hour / k_commit shift it left by id_bits).
+// Called for every piece of work that is launched under one Clock value (a single hour, a graph of <= 24 hours): when the
+// piece does not fit the current epoch the claim array is zeroed and the epoch restarts at the piece's first hour, so a
+// chunk of any length (epi_run_hours: up to RING_ROWS hours, 256 stamps at 10 M agents) is split at the stamp limit.
 int ensure_epoch(epi_engine* e, uint32_t first_hour, uint32_t last_hour) {
     const uint64_t limit = 1ull << (32 - e->P.id_bits);
+    if ((uint64_t)(last_hour - first_hour) + 1ull >= limit)
+        return engine_fail(e, EPI_ERR_STATE, "claim stamps: " + std::to_string(last_hour - first_hour + 1) + " hours under one clock do not fit " + std::to_string(32 - e->P.id_bits) + " stamp bits");
     const bool fits = !e->claim_dirty && first_hour >= e->epoch_base && (uint64_t)(last_hour - e->epoch_base) + 1ull < limit;
     if (!fits) {
         CU(cudaMemsetAsync(e->D.claim, 0, grid_alloc_bytes(e) * sizeof(uint32_t), e->stream));
         e->epoch_base = first_hour;
         e->claim_dirty = false;
+        e->epoch_resets++;
     }
     return EPI_OK;
 }
@@ -234,12 +240,13 @@ int queue_hours(epi_engine* e, uint32_t first_hour, uint32_t n, bool exchange_ho
     if (e->pend_kind.empty()) e->pend_first = first_hour;
     const uint32_t row0 = first_hour - e->pend_first;
     CU(cudaMemsetAsync(e->D.counts + (size_t)row0 * 8, 0, (size_t)n * 8 * sizeof(uint32_t), e->stream));
-    int rc = ensure_epoch(e, first_hour, first_hour + n - 1);
-    if (rc) return rc;
+    int rc = EPI_OK;
     uint32_t off = 0;
     while (off < n) {
         const uint32_t hour = first_hour + off;
         const uint32_t len = std::min(n - off, 24u);
+        rc = ensure_epoch(e, hour, hour + len - 1);
+        if (rc) return rc;
         {
             Timed t(e, KK_MISC);
             launch_set_clock(e->d_clock, Clock{hour, e->epoch_base, e->pend_first, 0}, e->stream);
@@ -316,14 +323,15 @@ int run_chunk(epi_engine* e, uint32_t first_hour, uint32_t n, bool inject, epi_c
         else return engine_fail(e, EPI_ERR_STATE, "hours are queued: call epi_collect_hours first");
     }
     CU(cudaMemsetAsync(e->D.counts, 0, (size_t)n * 8 * sizeof(uint32_t), e->stream));
-    int rc = ensure_epoch(e, first_hour, first_hour + n - 1);
-    if (rc) return rc;
+    int rc = EPI_OK;
     std::vector<uint8_t> ran(n, 0);  // hour produced its own counts row
     uint32_t off = 0;
     bool sleep_done = false;  // a k_sleep already ran in the current run of consecutive sleep hours
     while (off < n) {
         const uint32_t hour = first_hour + off;
         const bool aligned_day = !inject && !e->timing && e->graphs_enabled && hour % 24u == 1u && n - off >= 24u;
+        rc = ensure_epoch(e, hour, aligned_day ? hour + 23u : hour);
+        if (rc) return rc;
         {
             Timed t(e, KK_MISC);
             launch_set_clock(e->d_clock, Clock{hour, e->epoch_base, first_hour, 0}, e->stream);
@@ -565,8 +573,12 @@ int epi_create_multi(const epi_config* cfg_in, uint64_t seed, int device, int re
             const size_t R = (size_t)plan->n_regions;
             e->migration_row.assign(R, 0);
             e->commute_row.assign(R, 0);
-            if (e->migration_enabled) e->migration_row.assign(plan->migration + (size_t)region * R, plan->migration + (size_t)(region + 1) * R);
+            if (e->migration_enabled) {
+                e->migration_row.assign(plan->migration + (size_t)region * R, plan->migration + (size_t)(region + 1) * R);
+                e->migration_mat.assign(plan->migration, plan->migration + R * R);
+            }
             if (e->commute_enabled) {
+                e->commute_mat.assign(plan->commute, plan->commute + R * R);
                 e->commute_row.assign(plan->commute + (size_t)region * R, plan->commute + (size_t)(region + 1) * R);
                 apply_commute_plan(agents, n_agents, region, e->commute_row);
             }
@@ -651,6 +663,7 @@ void epi_destroy(epi_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
+    e->comm.reset();
     drop_graph(e);
     for (auto& pe : e->pending_events) { cudaEventDestroy(pe.second.first); cudaEventDestroy(pe.second.second); }
     void* ptrs[] = {e->D.cell, e->D.st, e->D.t0, e->D.home, e->D.work, e->D.wsa, e->D.prop, e->grid_alloc, e->D.claim, e->D.counts, e->D.tot,
@@ -658,6 +671,7 @@ void epi_destroy(epi_engine* e) {
     for (void* p : ptrs) if (p) cudaFree(p);
     for (void* p : e->travel_allocs) cudaFree(p);
     if (e->h_tv) cudaFreeHost(e->h_tv);
+    if (e->h_outgoing) cudaFreeHost(e->h_outgoing);
     if (e->h_counts) cudaFreeHost(e->h_counts);
     if (e->h_small) cudaFreeHost(e->h_small);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
@@ -713,6 +727,8 @@ int epi_reset(epi_engine* e) {
     initial_counts(e);
     e->interventions = epi::Interventions(e->cfg);
     e->events.clear();
+    e->outgoing_travels.clear();
+    e->outgoing_staged_hour = 0;
     return rebuild_grid(e);
 }
 
@@ -978,5 +994,6 @@ uint64_t epi_launch_count(const epi_engine* e, int reset) {
     return v;
 }
 uint64_t epi_device_bytes(const epi_engine* e) { return e ? e->device_bytes : 0; }
+uint64_t epi_epoch_resets(const epi_engine* e) { return e ? e->epoch_resets : 0; }
 
 }  // extern "C"

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <memory>
 #include <string>
 #include <utility>
 #include <vector>
@@ -11,6 +12,10 @@
 #include "host_model.h"
 #include "layout.h"
 #include "simulation.h"
+
+namespace epi {
+struct Comm;  // multi.h: the Transport of a multi-region engine
+}
 
 struct epi_engine {
     explicit epi_engine(const epi_config& c) : cfg(c), interventions(c) {}
@@ -34,6 +39,7 @@ struct epi_engine {
     // claim stamping
     uint32_t epoch_base = 0;
     bool claim_dirty = true;  // claim array needs zeroing before next use
+    uint64_t epoch_resets = 0;  // times the claim array was zeroed and the stamp epoch restarted (test hook: epi_epoch_resets)
     // day graph (hours h%24 = 1..23,0)
     cudaGraphExec_t day_graph = nullptr;
     uint32_t day_graph_launches = 0;
@@ -61,6 +67,14 @@ struct epi_engine {
     int n_regions = 1;
     bool migration_enabled = false, commute_enabled = false;
     std::vector<uint32_t> migration_row, commute_row;  // [to]
+    std::vector<uint32_t> migration_mat, commute_mat;  // the whole plan [from][to] (empty when disabled): sizes of the exchange segments
+    std::shared_ptr<epi::Comm> comm;                   // epi_comm_init / epi_comm_init_local
+    // TravelCounter (listeners/travel_counter.rs): outgoing migrators by destination and state, when asked for (epi_count_outgoing)
+    bool count_outgoing = false;
+    uint8_t* h_outgoing = nullptr;  // pinned copy of the send segments of a migration exchange
+    size_t h_outgoing_bytes = 0;
+    uint32_t outgoing_staged_hour = 0, outgoing_staged_stride = 0;
+    std::vector<epi_outgoing_travel> outgoing_travels;
     uint32_t start_migration_hour = 0, end_migration_hour = 0;
     // The reference's sequential bookkeeping of the exchange lives on the device (travel.cu): the free-slot stack (LIFO: arrivals
     // pop, departures push) and the house / office occupancy heaps (grid.rs:47-80, 279-341) as occupancy arrays in tie order.

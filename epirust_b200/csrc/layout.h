@@ -139,7 +139,7 @@ struct TravelVars {
     uint32_t err;        // TERR_* flags
     uint32_t n_in;       // arrivals of the exchange being unpacked
     uint32_t free_top;   // height of the free-slot stack
-    uint32_t pad;
+    uint32_t abort;      // err as k_travel_plan saw it: non-zero = this pack removes nobody
     uint32_t cnt[TRAVEL_MAX_REGIONS];   // records per destination region
     uint32_t base[TRAVEL_MAX_REGIONS];  // exclusive prefix of cnt
 };
@@ -163,6 +163,7 @@ struct TravelPtrs {
     uint32_t *bh_house, *pref_house, *bh_office, *pref_office;  // per-block occupancy histograms and per-level block prefixes
     FillPlan *plan_house, *plan_office;
     int n_regions;
+    const uint32_t* seg_cap;  // records (header included) the segment of each destination may hold, or nullptr = the stride
 };
 
 struct Clock {           // device-resident so CUDA graphs can be replayed for any day

@@ -160,7 +160,7 @@ int run_single_engine(epi_engine* e, const epi_config& cfg, RunResult& result, b
 }
 
 // ---- config JSON (common::config::Config, common/src/config/mod.rs:44-58) ------------------------------------------
-static void config_from_value(const JsonValue& root, epi_config& c) {
+void config_from_value(const JsonValue& root, epi_config& c) {
     std::memset(&c, 0, sizeof(c));
     const JsonValue& pop = root.at("population");
     if (const JsonValue* a = pop.find("Auto")) {

@@ -103,6 +103,10 @@ struct RunResult {
     std::string csv_path, interventions_path;
 };
 
+struct JsonValue;
+// common::config::Config from its JSON object (common/src/config/mod.rs:44-58); throws std::runtime_error
+void config_from_value(const JsonValue& root, epi_config& c);
+
 // process_interventions on one Counts row (host decisions + the sweep kernels)
 int process_interventions(epi_engine* e, const epi_counts& c, bool log);
 

@@ -110,6 +110,10 @@ int epi_travel_pack(epi_engine* e, uint32_t hour, int kind, void* send_buf, uint
         for (uint32_t v : e->migration_row) planned_total += v;
         if (!e->migration_enabled || h != 0 || !(hour > e->start_migration_hour && hour < e->end_migration_hour) || planned_total == 0 || e->population == 0)
             return write_empty_headers(e, send_buf, stride_records);
+        // gen_bool(percent_outgoing) panics for p > 1 (rand 0.8 Bernoulli::new; allocation_map.rs:110): an error here
+        if (planned_total > e->population)
+            return engine_fail(e, EPI_ERR_STATE, "migration plan row (" + std::to_string(planned_total) + " outgoing) exceeds the region's population (" +
+                                                     std::to_string(e->population) + "): percent_outgoing > 1");
         A.thr_outgoing = bernoulli_threshold((double)planned_total / (double)e->population);
     } else if (!e->commute_enabled || !(h == 7 || h == 17)) {
         return write_empty_headers(e, send_buf, stride_records);

@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(1024) k_travel_scan(uint32_t* __restrict__ blo
     }
     if (threadIdx.x == 0) {
         tv->total = carry;
-        tv->n_send = 0; tv->n_working = 0; tv->pending = 0;
+        tv->n_send = 0; tv->n_working = 0; tv->pending = 0; tv->abort = 0;
     }
 }
 
@@ -219,12 +219,19 @@ __global__ void __launch_bounds__(1024) k_travel_plan(Params P, TravelArgs A, Tr
     }
     __syncthreads();
     for (uint32_t to = threadIdx.x; to < R; to += blockDim.x) {
-        if (tv->cnt[to] + 1u > stride) atomicOr(&tv->err, TERR_SEGMENT_OVERFLOW);
+        if (tv->cnt[to] + 1u > (T.seg_cap ? min(T.seg_cap[to], stride) : stride)) atomicOr(&tv->err, TERR_SEGMENT_OVERFLOW);
         TravelRecord h{};
         h.st = min(tv->cnt[to], stride - 1u);  // header: records in this segment
         h.from = (uint32_t)P.region;
         send[(size_t)to * stride] = h;
     }
+    // A list or segment overflow is known by now: k_travel_pack then removes nobody (the region stays intact, the host reports
+    // the error), and the headers promise no records.
+    __syncthreads();
+    if (threadIdx.x == 0) tv->abort = tv->err;
+    __syncthreads();
+    if (tv->err)
+        for (uint32_t to = threadIdx.x; to < R; to += blockDim.x) send[(size_t)to * stride].st = 0;
 }
 
 // commuters: list_pos[p] = number of earlier candidates with the same destination (block d serves destination d)
@@ -249,7 +256,7 @@ __global__ void __launch_bounds__(256) k_travel_pack(Params P, DevPtrs D, Travel
     TravelVars* tv = T.tv;
     const uint32_t free_top = tv->free_top;
     const uint32_t total = min(tv->total, T.list_cap);
-    if (p >= total) return;
+    if (p >= total || tv->abort) return;
     uint32_t dest, j;
     if (A.kind == TRAVEL_MIGRATE) {
         if (p >= tv->n_send) return;  // surplus candidates stay
@@ -285,7 +292,7 @@ __global__ void __launch_bounds__(256) k_travel_pack(Params P, DevPtrs D, Travel
 // the free-slot stack grows by the leavers (after k_travel_pack) / shrinks by the arrivals (after the last placement round)
 __global__ void k_travel_stack_moved(TravelVars* tv, int arrivals) {
     if (arrivals) tv->free_top -= tv->n_in;
-    else tv->free_top += tv->n_send;
+    else if (!tv->abort) tv->free_top += tv->n_send;
 }
 
 // ---- arriving -----------------------------------------------------------------------------------------------------------

@@ -91,7 +91,9 @@ class Engine:
         self.L = _ffi.load()
         self.cfg = cfg
         h = C.c_void_p()
-        if plan is None:
+        if plan is None and extra_capacity:  # a standalone engine with empty agent slots (tests: a wide id field in the claim words)
+            rc = self.L.epi_create_multi(C.byref(cfg), seed, device, region, None, extra_capacity, C.byref(h))
+        elif plan is None:
             rc = self.L.epi_create_region(C.byref(cfg), seed, device, region, C.byref(h))
         else:
             R = int(plan["n_regions"])
@@ -281,6 +283,10 @@ class Engine:
     @property
     def device_bytes(self):
         return int(self.L.epi_device_bytes(self.h))
+
+    @property
+    def epoch_resets(self):
+        return int(self.L.epi_epoch_resets(self.h))
 
 
 def population_size(cfg):

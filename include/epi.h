@@ -198,6 +198,61 @@ int epi_finish_hour(epi_engine* e, uint32_t hour, epi_counts* out);
 /* home region | work region << 8 per agent slot (0 for empty slots): Area.location_id of home_location / work_location */
 int epi_get_regions(epi_engine* e, uint32_t* reg);
 
+/* ---- multi-region: the Transport and the hour loop behind the ABI ---------------------------------------------------------
+ * Replaces the reference's `Transport` trait (engine/src/transport/mod.rs:34-42) and its MPI implementation
+ * (MpiTransport::send_commuters / send_migrators / receive_commuters / receive_migrators, transport/mpi_transport.rs:78-215:
+ * bincode + snappy over MPI point-to-point) by an all-to-allv of packed 32-byte records between the GPUs: NCCL grouped
+ * ncclSend / ncclRecv over NVLink / NVSwitch, one rank per region, everything queued on the engine's stream (pack kernels ->
+ * collective -> unpack kernels, no host wait in between).  Each (source, destination) pair ships only the records the travel
+ * plan can produce for it (the commute matrix entry; the migration matrix entry + 8 sigma), not a padded segment.
+ *
+ * epi_comm_unique_id: ncclGetUniqueId.  One rank calls it and hands the EPI_COMM_ID_BYTES bytes to the others by any means
+ *   (a file, an environment variable, MPI_Bcast: the reference's ranks meet through mpirun, engine-app/src/main.rs:131-147).
+ * epi_comm_init: ncclCommInitRank on the engine's device; rank must equal the engine's region index, n_ranks the number of
+ *   regions of its travel plan (MpiTransport::new, mpi_transport.rs:44-52).  Allocates the send / receive segments.
+ * epi_comm_init_local: every region of the plan lives in this process (tests; several regions on one GPU, or one process
+ *   driving several GPUs): the "collective" is a set of device-to-device copies ordered by CUDA events.
+ * Failures of NCCL itself return EPI_ERR_NCCL with ncclGetErrorString in epi_last_error. */
+#define EPI_COMM_ID_BYTES 128
+int epi_comm_unique_id(void* id_out);
+int epi_comm_init(epi_engine* e, int n_ranks, int rank, const void* unique_id);
+int epi_comm_init_local(epi_engine* const* engines, int n_engines);
+int epi_comm_destroy(epi_engine* e);
+/* EPI_TRAVEL_MIGRATE / EPI_TRAVEL_COMMUTE when `hour` is an exchange hour of this engine's travel plan, -1 otherwise
+ * (MpiTransport::receive_tick, mpi_transport.rs:60-76; migrators only inside the migration window, citizen/mod.rs:460-462) */
+int epi_exchange_kind(const epi_engine* e, uint32_t hour);
+/* One traveller exchange on an engine with an NCCL communicator: epi_travel_pack -> all-to-allv -> epi_travel_unpack, all
+ * deferred (epi_finish_hour settles).  Every rank of the communicator must call it for the same (hour, kind).  The body of
+ * epidemiology_simulation.rs:407-488. */
+int epi_exchange(epi_engine* e, uint32_t hour, int kind);
+/* Epidemiology::run_multi_engine's hour loop (epidemiology_simulation.rs:331-537) for hours first_hour .. first_hour +
+ * n_hours - 1 of the n_local engines this process hosts (1 with epi_comm_init, all regions with epi_comm_init_local):
+ * the plain hours between two exchanges are queued as CUDA graphs, the exchange hour's kernels, pack, collective and unpack
+ * follow on the same stream, and the host waits once per exchange / decision hour.  rows_out[n_local][n_hours].
+ * terminate_when_clear != 0 adds the orchestrator's global termination rule (orchestrator/src/ticks.rs:35-89, 175-180; Kafka
+ * mode -- MPI mode always runs to `hours`): at every tick hour (hour 1 and the hours of day 0 / 7 / 17 whose exchange kind is
+ * enabled) the regions' exposed + infected + hospitalized are summed over all ranks; when the sum is zero the run stops
+ * before the next tick hour.  *n_rows = hours executed (the same on every rank). */
+int epi_run_multi_hours(epi_engine* const* engines, int n_local, uint32_t first_hour, uint32_t n_hours, int terminate_when_clear, epi_counts* rows_out,
+                        uint32_t* n_rows);
+/* TravelCounter (engine/src/listeners/travel_counter.rs:27-92): one CountsByRegion per destination the plan sends migrators to,
+ * at every hour % 24 == 0 of a migration-enabled run.  epi_count_outgoing(e, 1) turns the listener on (the used part of the send
+ * segments then also goes to the host behind the pack kernels); epi_outgoing_travels reads what accumulated since epi_create /
+ * epi_reset (out may be NULL to query *n). */
+typedef struct epi_outgoing_travel {
+    uint32_t hr, destination, susceptible, exposed, infected, recovered; /* destination: region index in the travel plan */
+} epi_outgoing_travel;
+int epi_count_outgoing(epi_engine* e, int on);
+int epi_outgoing_travels(const epi_engine* e, epi_outgoing_travel* out, uint32_t max_rows, uint32_t* n);
+/* TickAcks::should_terminate (orchestrator/src/ticks.rs:175-180) on the Counts the regions acknowledged for one tick: 1 when
+ * no region has exposed, infected or hospitalized agents.  Host only. */
+int epi_should_terminate(const epi_counts* acks, int n_acks);
+/* Host only (no GPU): the order in which epi_run_multi_hours queues work for one region whose decision hours are start of day
+ * plus `vaccinate_hours` / `unlock_hour` (0 = none), written to `out` as text, one call per line ("hours F N", "exchange_hour
+ * H", "exchange H KIND", "collect", "finish H").  Test hook of the scheduling logic. */
+int epi_multi_schedule_trace(const epi_travel_plan* plan, const uint32_t* vaccinate_hours, int n_vaccinate, uint32_t unlock_hour, uint32_t first_hour,
+                             uint32_t n_hours, char* out, uint64_t out_bytes);
+
 /* ---- interventions: the O(N) sweeps; the decisions stay with the host (interventions/ *.rs) ---------------- */
 /* CitizenLocationMap::lock_city (allocation_map.rs:349-356) */
 int epi_lock_city(epi_engine* e);
@@ -241,6 +296,10 @@ int epi_get_kernel_times(epi_engine* e, double* ms_total, uint64_t* launches);
 uint64_t epi_launch_count(const epi_engine* e, int reset);
 /* device bytes held by the engine */
 uint64_t epi_device_bytes(const epi_engine* e);
+/* How often the claim array was zeroed because the hour stamps of the claim words (32 - id_bits bits, id_bits =
+ * ceil(log2(agent slots))) were used up: 255 hours at 10 M agents.  epi_run_hours / epi_enqueue_hours split their work at
+ * that limit.  (No reference equivalent: the reference clears its `upcoming` map every hour, allocation_map.rs:131-134.) */
+uint64_t epi_epoch_resets(const epi_engine* e);
 
 /* ---- host driver: the engine-app equivalent ----------------------------------------------------------------- */
 /* Parse the reference's simulation-config JSON (common::config::Config::read, common/src/config/mod.rs:124-128). */
@@ -254,6 +313,32 @@ int epi_config_from_json_string(const char* json_text, epi_config* out);
  * hour-loop wall time (what the reference logs as Iterations/sec, epidemiology_simulation.rs:270-272). */
 int epi_run_standalone(const epi_config* cfg, uint64_t seed, int device, const char* output_dir, const char* engine_id,
                        epi_counts* rows_out, uint32_t max_rows, uint32_t* n_rows, double* loop_seconds);
+
+/* ---- host driver: multi-region runs (engine-app -m mpi) ----------------------------------------------------------------- */
+/* common::config::Configuration (common/src/config/configuration.rs:28-57): {engine_configs: [{engine_id, config}],
+ * travel_plan: {regions, migration: {enabled, matrix, start_migration_hour, end_migration_hour}, commute: {enabled, matrix}}}.
+ * epi_configuration_read = Configuration::read + TravelPlanConfig::validate_regions (travel_plan_config.rs:60-62) +
+ * Configuration::validate (configuration.rs:59-117); what the reference panics on comes back as EPI_ERR_CONFIG.  Regions are
+ * named by their index in travel_plan.regions == rank (MpiTransport::new, transport/mpi_transport.rs:44-52). */
+typedef struct epi_configuration epi_configuration;
+int epi_configuration_read(const char* json_path, epi_configuration** out);
+void epi_configuration_free(epi_configuration* c);
+int epi_configuration_regions(const epi_configuration* c);
+const char* epi_configuration_region_name(const epi_configuration* c, int region);
+/* the Config of the engine whose engine_id names `region` */
+int epi_configuration_engine_config(const epi_configuration* c, int region, epi_config* out);
+/* the travel plan restricted to its first n_regions regions; migration_out / commute_out: n_regions x n_regions words each that
+ * the returned plan points to */
+int epi_configuration_travel_plan(const epi_configuration* c, int n_regions, epi_travel_plan* out, uint32_t* migration_out, uint32_t* commute_out);
+/* agent slots epi_run_region reserves for the arrivals of `region` (every commuter of a day + the migrators of the window) */
+uint32_t epi_configuration_arrival_capacity(const epi_configuration* c, int region);
+/* One rank of `engine-app -m mpi` (engine-app/src/main.rs:131-166: rank r takes engine_configs[r], EngineApp::start_with_mpi,
+ * Epidemiology::run_multi_engine): creates region `region` of the first n_ranks regions on `device` with Philox key seed +
+ * region, joins the communicator `unique_id` names (epi_comm_unique_id), runs hours 1 .. config.hours - 1 and writes
+ * <output_dir>/output/simulation_<engine_id>_<UTC>.csv, ..._interventions.json, ..._outgoing_travels.csv (output_dir may be
+ * NULL).  terminate_when_clear: see epi_run_multi_hours. */
+int epi_run_region(const epi_configuration* c, int region, int n_ranks, const void* unique_id, uint64_t seed, int device, const char* output_dir,
+                   int terminate_when_clear, epi_counts* rows_out, uint32_t max_rows, uint32_t* n_rows, double* loop_seconds);
 
 const char* epi_version(void);
 
