@@ -195,7 +195,7 @@ def run_ours(args):
     import torch.distributed as dist
 
     from epirust_b200.engine import Engine, make_config, STATE_FIELDS, STATE_DTYPES
-    from epirust_b200.multi import DistExchange, MultiRegion
+    from epirust_b200.multi import MultiRegion, max_over_ranks, share_unique_id
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -226,14 +226,17 @@ def run_ours(args):
         if not multi:
             got, _ = eng.simulate_hours(first_hour, n_hours, out=out)
             return got
-        return runner.run(first_hour, n_hours, rows_out=out[None])[0]
+        got = runner.run(first_hour, n_hours)[0]
+        out[: len(got)] = got
+        return got
 
     sampler = ClockSampler(local)
     # ---------------- value: state resident in HBM ----------------
     rows = np.zeros((24 * (K + W), 7), np.uint32)
     with torch.cuda.stream(stream):
         if multi:
-            runner = MultiRegion([eng], plan, exchange=DistExchange(torch.device("cuda", local)), stride_records=2 * (n // 1000) + 4096)
+            # the ranks' NCCL communicator lives behind the C ABI (epi_comm_init); torch.distributed only carries its unique id
+            runner = MultiRegion([eng], n_ranks=world, rank=rank, unique_id=share_unique_id(dist, device=torch.device("cuda", local)))
         simulate(1, 24 * W, rows)  # warm-up days (also builds the day graph)
         barrier()
         if rank == 0:
@@ -251,10 +254,7 @@ def run_ours(args):
         clocks = sampler.stop() if rank == 0 else None
     assert len(got) == 24 * K
     last_row = [int(v) for v in got[-1]]
-    t = torch.tensor([ms, (t_wall1 - t_wall0) * 1e3], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max, wall_ms_max = float(t[0].item()), float(t[1].item())
+    ms_max, wall_ms_max = max_over_ranks(dist, [ms, (t_wall1 - t_wall0) * 1e3], device="cuda") if world > 1 else (ms, (t_wall1 - t_wall0) * 1e3)
     value = world * n * 24.0 * K / (ms_max * 1e-3)
 
     # ---------------- per-kernel durations over the SAME simulated days (CUDA events around every launch, graphs off) ----
@@ -307,6 +307,8 @@ def run_ours(args):
         e2e = {"value": world * n * 24.0 * K / (wall_ms_max * 1e-3), "unit": "agent-steps/s", "h2d_bytes_per_step": 0,
                "d2h_bytes_per_step": 24 * 28 + 3 * (4 * (8 + world) + 4 * 32 * 8),
                "note": "host wall clock around the timed K days (max over ranks); the state stays in HBM (a region has no per-day host input), per day the 24 Counts rows come back and, per exchange, the exchange's scalars (TravelVars) and the running Counts totals; traveller records go GPU to GPU"}
+    if runner is not None:
+        runner.close()
     eng.close()
 
     cpu = None
@@ -330,7 +332,7 @@ def run_ours(args):
             "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": wl, "agents_per_gpu": n, "grid_size": kw["grid_size"], "step": "one simulated day (24 hours)",
                        "l2": "state + grids larger than L2 (no flush needed)" if n >= 5_000_000 else "working set fits the 126 MB L2; no flush (the real run is L2-resident too)",
-                       "regions": world, "exchange": "one NCCL all_to_all_single of padded segments (count in the segment header) at h%24 in {0, 7, 17}" if multi else "n/a", "last_counts_row": last_row},
+                       "regions": world, "exchange": "epi_exchange: pack -> grouped ncclSend/ncclRecv of the plan-bounded segments (count in the segment header) -> unpack, at h%24 in {0, 7, 17}" if multi else "n/a", "last_counts_row": last_row},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)

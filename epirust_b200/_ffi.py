@@ -59,6 +59,7 @@ class EpiTravelPlan(C.Structure):
                 ("commute", C.c_void_p), ("start_migration_hour", C.c_uint32), ("end_migration_hour", C.c_uint32)]
 
 
+COMM_ID_BYTES = 128
 TRAVEL_RECORD_BYTES = 32
 TRAVEL_MIGRATE, TRAVEL_COMMUTE = 0, 1
 
@@ -74,10 +75,33 @@ EXPORTS = [
     "epi_sync", "epi_reset", "epi_step", "epi_enqueue_hour", "epi_enqueue_hours", "epi_collect_hours", "epi_next_decision_hour", "epi_step_with_draws", "epi_run_hours", "epi_simulate_hours", "epi_intervention_events", "epi_lock_city", "epi_unlock_city", "epi_vaccinate",
     "epi_expand_hospital", "epi_get_state", "epi_set_state", "epi_build_population", "epi_population_size", "epi_geometry", "epi_get_grid", "epi_set_kernel_timing",
     "epi_get_kernel_times", "epi_launch_count", "epi_device_bytes", "epi_epoch_resets", "epi_config_from_json", "epi_config_from_json_string",
-    "epi_run_standalone", "epi_version",
+    "epi_run_standalone", "epi_version", "epi_device_count",
+    "epi_comm_unique_id", "epi_comm_init", "epi_comm_init_local", "epi_comm_destroy", "epi_exchange_kind", "epi_exchange", "epi_run_multi_hours",
+    "epi_count_outgoing", "epi_outgoing_travels", "epi_should_terminate", "epi_multi_schedule_trace",
+    "epi_configuration_read", "epi_configuration_free", "epi_configuration_regions", "epi_configuration_region_name", "epi_configuration_engine_config",
+    "epi_configuration_travel_plan", "epi_configuration_arrival_capacity", "epi_run_region", "epi_write_outputs",
 ]
 
 _lib = None
+
+
+def _preload_bundled_nccl():
+    """libepirust_b200.so links libnccl.so.2 (the traveller exchange).  PyTorch wheels ship their own, newer libnccl.so.2 and
+    libtorch_cuda.so needs symbols only that one has: whichever copy a process loads first serves both.  So in a Python process
+    that might import torch later (tests, bench.py) the bundled copy is loaded first when it exists; a process without PyTorch
+    (the engine-app binary) uses the system library."""
+    import importlib.util
+
+    try:
+        spec = importlib.util.find_spec("nvidia.nccl")
+    except (ImportError, ValueError):
+        spec = None
+    for d in (spec.submodule_search_locations if spec and spec.submodule_search_locations else []):
+        p = os.path.join(d, "lib", "libnccl.so.2")
+        if os.path.exists(p):
+            C.CDLL(p, mode=C.RTLD_GLOBAL)
+            return p
+    return None
 
 
 def load():
@@ -89,6 +113,7 @@ def load():
         raise RuntimeError(
             f"{LIB_PATH} is missing: build it with `python -m epirust_b200.build` (nvcc, sm_100a). "
             "epirust_b200 has no CPU fallback.")
+    _preload_bundled_nccl()
     L = C.CDLL(LIB_PATH)
     vp, u32, u64, i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int
     L.epi_create.argtypes = [C.POINTER(EpiConfig), u64, i32, C.POINTER(vp)]
@@ -142,5 +167,28 @@ def load():
     L.epi_config_from_json_string.argtypes = [C.c_char_p, C.POINTER(EpiConfig)]
     L.epi_run_standalone.argtypes = [C.POINTER(EpiConfig), u64, i32, C.c_char_p, C.c_char_p, vp, u32, C.POINTER(u32), C.POINTER(C.c_double)]
     L.epi_version.restype = C.c_char_p
+    L.epi_comm_unique_id.argtypes = [vp]
+    L.epi_comm_init.argtypes = [vp, i32, i32, vp]
+    L.epi_comm_init_local.argtypes = [vp, i32]
+    L.epi_comm_destroy.argtypes = [vp]
+    L.epi_exchange_kind.argtypes = [vp, u32]
+    L.epi_exchange.argtypes = [vp, u32, i32]
+    L.epi_run_multi_hours.argtypes = [vp, i32, u32, u32, i32, vp, C.POINTER(u32)]
+    L.epi_count_outgoing.argtypes = [vp, i32]
+    L.epi_outgoing_travels.argtypes = [vp, vp, u32, C.POINTER(u32)]
+    L.epi_should_terminate.argtypes = [vp, i32]
+    L.epi_multi_schedule_trace.argtypes = [C.POINTER(EpiTravelPlan), vp, i32, u32, u32, u32, C.c_char_p, u64]
+    L.epi_configuration_read.argtypes = [C.c_char_p, C.POINTER(vp)]
+    L.epi_configuration_free.argtypes = [vp]
+    L.epi_configuration_free.restype = None
+    L.epi_configuration_regions.argtypes = [vp]
+    L.epi_configuration_region_name.argtypes = [vp, i32]
+    L.epi_configuration_region_name.restype = C.c_char_p
+    L.epi_configuration_engine_config.argtypes = [vp, i32, C.POINTER(EpiConfig)]
+    L.epi_configuration_travel_plan.argtypes = [vp, i32, C.POINTER(EpiTravelPlan), vp, vp]
+    L.epi_configuration_arrival_capacity.argtypes = [vp, i32]
+    L.epi_configuration_arrival_capacity.restype = u32
+    L.epi_run_region.argtypes = [vp, i32, i32, vp, u64, i32, C.c_char_p, i32, vp, u32, C.POINTER(u32), C.POINTER(C.c_double)]
+    L.epi_write_outputs.argtypes = [C.c_char_p, C.c_char_p, vp, u32, vp, u32, vp, u32, vp, C.c_char_p, u64]
     _lib = L
     return L

@@ -16,7 +16,7 @@ CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libepirust_b200.so")
 APP = os.path.join(PKG, "engine-app")
 
-LIB_SOURCES = ["kernels.cu", "travel.cu", "engine.cpp", "host_model.cpp", "json.cpp", "simulation.cpp", "travel.cpp"]
+LIB_SOURCES = ["kernels.cu", "travel.cu", "engine.cpp", "host_model.cpp", "json.cpp", "simulation.cpp", "travel.cpp", "multi.cpp", "configuration.cpp"]
 APP_SOURCES = ["engine_app_main.cpp"]
 
 NVCC_FLAGS = [
@@ -58,7 +58,8 @@ def build(force=False, verbose=False):
                     print(" ".join(cmd))
                 subprocess.check_call(cmd)
             objs.append(o)
-        cmd = [nvcc, "-shared", "-ccbin", "/usr/bin/g++", "-Xcompiler", "-fopenmp", "-o", LIB] + objs
+        # libnccl: the traveller exchange of multi-region runs (csrc/multi.cpp)
+        cmd = [nvcc, "-shared", "-ccbin", "/usr/bin/g++", "-Xcompiler", "-fopenmp", "-o", LIB] + objs + ["-lnccl"]
         if verbose:
             print(" ".join(cmd))
         subprocess.check_call(cmd)

@@ -127,26 +127,37 @@ uint32_t arrival_capacity(const epi_configuration& c, size_t r, uint32_t hours) 
 
 // CsvListener, InterventionReporter and TravelCounter at simulation_ended (listeners/csv_service.rs:44-71,
 // intervention_reporter.rs:28-63, travel_counter.rs:69-79)
-void write_region_outputs(const std::string& base, const std::vector<epi_counts>& rows, epi_engine* e, const epi_configuration& c) {
+void write_outputs(const std::string& base, const epi_counts* rows, uint32_t n_rows, const epi_intervention_event* ev, uint32_t n_events,
+                   const epi_outgoing_travel* tr, uint32_t n_travels, const std::vector<std::string>* region_names) {
     Listeners l;
-    l.counts = rows;
-    uint32_t n_events = 0;
-    epi_intervention_events(e, nullptr, 0, &n_events);
-    std::vector<epi_intervention_event> ev(n_events);
-    if (n_events) epi_intervention_events(e, ev.data(), n_events, &n_events);
+    l.counts.assign(rows, rows + n_rows);
     static const char* names[3] = {"lockdown", "vaccination", "build_new_hospital"};
-    for (const epi_intervention_event& x : ev)
+    for (uint32_t i = 0; i < n_events; ++i) {
+        const epi_intervention_event& x = ev[i];
+        if (x.kind < 0 || x.kind > 2) throw std::runtime_error("intervention event of unknown kind");
         l.interventions.push_back({x.hour, names[x.kind], x.kind == 0 ? (x.status ? "{\"status\":\"locked_down\"}" : "{\"status\":\"lockdown_revoked\"}") : "{}"});
+    }
     l.simulation_ended(base);
-    uint32_t n_travels = 0;
-    epi_outgoing_travels(e, nullptr, 0, &n_travels);
-    std::vector<epi_outgoing_travel> tr(n_travels);
-    if (n_travels) epi_outgoing_travels(e, tr.data(), n_travels, &n_travels);
+    if (!region_names) return;
     std::ofstream f(base + "_outgoing_travels.csv");
     if (!f) throw std::runtime_error("Failed to write to file " + base + "_outgoing_travels.csv");
     if (n_travels) f << "hr,destination,susceptible,exposed,infected,recovered\n";  // csv::Writer::serialize writes the header with the first record
-    for (const epi_outgoing_travel& t : tr)
-        f << t.hr << ',' << c.regions[t.destination] << ',' << t.susceptible << ',' << t.exposed << ',' << t.infected << ',' << t.recovered << '\n';
+    for (uint32_t i = 0; i < n_travels; ++i) {
+        const epi_outgoing_travel& t = tr[i];
+        if (t.destination >= region_names->size()) throw std::runtime_error("outgoing travel to an unknown region");
+        f << t.hr << ',' << (*region_names)[t.destination] << ',' << t.susceptible << ',' << t.exposed << ',' << t.infected << ',' << t.recovered << '\n';
+    }
+}
+
+void write_region_outputs(const std::string& base, const std::vector<epi_counts>& rows, epi_engine* e, const epi_configuration& c) {
+    uint32_t n_events = 0, n_travels = 0;
+    epi_intervention_events(e, nullptr, 0, &n_events);
+    std::vector<epi_intervention_event> ev(n_events);
+    if (n_events) epi_intervention_events(e, ev.data(), n_events, &n_events);
+    epi_outgoing_travels(e, nullptr, 0, &n_travels);
+    std::vector<epi_outgoing_travel> tr(n_travels);
+    if (n_travels) epi_outgoing_travels(e, tr.data(), n_travels, &n_travels);
+    write_outputs(base, rows.data(), (uint32_t)rows.size(), ev.data(), n_events, tr.data(), n_travels, &c.regions);
 }
 
 }  // namespace
@@ -203,6 +214,30 @@ int epi_configuration_travel_plan(const epi_configuration* c, int n_regions, epi
     out->commute = commute_out;
     out->start_migration_hour = c->start_migration_hour;
     out->end_migration_hour = c->end_migration_hour;
+    return EPI_OK;
+}
+
+int epi_write_outputs(const char* output_dir, const char* engine_id, const epi_counts* rows, uint32_t n_rows, const epi_intervention_event* events,
+                      uint32_t n_events, const epi_outgoing_travel* travels, uint32_t n_travels, const char* const* region_names, char* base_out,
+                      uint64_t base_bytes) {
+    if (!output_dir || !engine_id || (!rows && n_rows) || (!events && n_events) || (travels && !region_names))
+        return engine_fail(nullptr, EPI_ERR_ARG, "epi_write_outputs: null argument");
+    try {
+        const std::string base = output_file_format(output_dir, engine_id);
+        std::vector<std::string> names;
+        if (travels) {
+            uint32_t most = 0;
+            for (uint32_t i = 0; i < n_travels; ++i) most = std::max(most, travels[i].destination + 1u);
+            for (uint32_t r = 0; r < most; ++r) names.push_back(region_names[r]);
+        }
+        write_outputs(base, rows, n_rows, events, n_events, travels, n_travels, travels ? &names : nullptr);
+        if (base_out) {
+            if (base.size() + 1 > base_bytes) return engine_fail(nullptr, EPI_ERR_ARG, "epi_write_outputs: base_out too small");
+            std::memcpy(base_out, base.c_str(), base.size() + 1);
+        }
+    } catch (const std::exception& ex) {
+        return engine_fail(nullptr, EPI_ERR_IO, ex.what());
+    }
     return EPI_OK;
 }
 

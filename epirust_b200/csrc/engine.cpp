@@ -502,7 +502,12 @@ void initial_counts(epi_engine* e) {
 
 extern "C" {
 
-const char* epi_version(void) { return "epirust_b200 0.1 (sm_100a)"; }
+const char* epi_version(void) { return "epirust_b200 0.2 (sm_100a)"; }
+
+int epi_device_count(void) {
+    int n = 0;
+    return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;
+}
 
 const char* epi_last_error(const epi_engine* e) {
     if (e) return e->err.c_str();

@@ -7,11 +7,15 @@
 // --seed (Philox key; the reference is unseeded) and --device.
 //   standalone  Config::read(FILE or config/default.json) -> EngineApp::start_standalone (engine_app.rs:89-106); writes
 //               <OUTPUT_DIR>/output/simulation_0_<UTC>.csv and ..._interventions.json.
-//   mpi         one region engine per GPU: re-launches `python -m epirust_b200.engine_app` under torch.distributed.run with
-//               one process per region (the reference is started with `mpirun -n <regions>`, main.rs:131-166).
+//   mpi         one region engine per GPU, one process per region (the reference is started with `mpirun -n <regions>`,
+//               main.rs:131-166): forks the region processes itself, or is one rank when RANK / WORLD_SIZE are set; the ranks
+//               exchange travellers over NCCL (epi_run_region).  No Python anywhere on this path.
 //   kafka       not available (needs a Kafka broker; the orchestrator's tick barrier is replaced by the collective).
+#include <signal.h>
+#include <sys/wait.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -29,6 +33,7 @@ struct Args {
     unsigned long long seed = 1;
     int device = 0;
     int nproc = 0;  // mpi mode: processes to launch (0 = number of regions in the config)
+    bool terminate_when_clear = false;  // mpi mode: the orchestrator's global termination rule (ticks.rs:175-180)
 };
 
 void usage(FILE* f) {
@@ -44,6 +49,8 @@ void usage(FILE* f) {
                  "      --seed <SEED>              Philox key of the run [default: 1]\n"
                  "      --device <DEVICE>          CUDA device of a standalone run [default: 0]\n"
                  "      --nproc <N>                mpi mode: regions (= GPUs = processes) to run [default: all regions of the config]\n"
+                 "      --terminate-when-clear     mpi mode: stop when no region has exposed / infected / hospitalized agents (the\n"
+                 "                                 orchestrator's rule in Kafka mode; the reference's MPI mode runs to `hours`)\n"
                  "  -h, --help                     Print help\n"
                  "  -V, --version                  Print version\n");
 }
@@ -77,6 +84,7 @@ int parse(int argc, char** argv, Args& a) {
         else if (k == "--seed") { if (!value(s)) return 2; a.seed = std::strtoull(s.c_str(), nullptr, 10); }
         else if (k == "--device") { if (!value(s)) return 2; a.device = std::atoi(s.c_str()); }
         else if (k == "--nproc") { if (!value(s)) return 2; a.nproc = std::atoi(s.c_str()); }
+        else if (k == "--terminate-when-clear") a.terminate_when_clear = true;
         else { std::fprintf(stderr, "error: unexpected argument '%s' found\n\n", k.c_str()); usage(stderr); return 2; }
     }
     return 0;
@@ -101,24 +109,104 @@ int run_standalone(const Args& a) {
     return 0;
 }
 
-int run_mpi(const Args& a, const char* argv0) {
-    // one process per region under torch.distributed.run; the Python launcher mirrors main.rs:131-166
+// ---- -m mpi: one process per region, one region per GPU ---------------------------------------------------------------
+// The reference is started as `mpirun -n <regions> engine-app -m mpi` and its ranks meet through MPI (main.rs:131-147).  Here
+// the ranks meet through an NCCL communicator whose unique id travels in a file:
+//   * started under a launcher that sets RANK and WORLD_SIZE (torchrun, mpirun wrappers, SLURM scripts): this process is that
+//     rank; the id file is $EPI_COMM_ID_FILE (default /tmp/epi_comm_<MASTER_PORT>.id), written by rank 0;
+//   * started plainly: engine-app forks one child per region (before any CUDA call) and waits for them.
+// Rank r runs region r = travel_plan.regions[r] on GPU r % device_count.  `-i/--id` is accepted and unused like in the
+// reference's MPI arm (the engine id comes from the config, main.rs:146-151; only Kafka mode reads --id).
+bool write_id_file(const std::string& path) {
+    unsigned char id[EPI_COMM_ID_BYTES];
+    if (epi_comm_unique_id(id) != EPI_OK) { std::fprintf(stderr, "engine-app: %s\n", epi_last_error(nullptr)); return false; }
+    const std::string tmp = path + ".tmp";
+    FILE* f = std::fopen(tmp.c_str(), "wb");
+    if (!f || std::fwrite(id, 1, sizeof(id), f) != sizeof(id)) { std::perror("engine-app: cannot write the communicator id file"); if (f) std::fclose(f); return false; }
+    std::fclose(f);
+    return std::rename(tmp.c_str(), path.c_str()) == 0;
+}
+
+bool read_id_file(const std::string& path, unsigned char* id) {
+    for (int tries = 0; tries < 6000; ++tries) {  // up to 10 minutes: rank 0 may still be paging the CUDA libraries in
+        FILE* f = std::fopen(path.c_str(), "rb");
+        if (f) {
+            const size_t n = std::fread(id, 1, EPI_COMM_ID_BYTES, f);
+            std::fclose(f);
+            if (n == EPI_COMM_ID_BYTES) return true;
+        }
+        usleep(100 * 1000);
+    }
+    std::fprintf(stderr, "engine-app: timed out waiting for the communicator id file %s\n", path.c_str());
+    return false;
+}
+
+int run_rank(const Args& a, const epi_configuration* cfg, int rank, int world, const std::string& id_file) {
+    std::printf("MPI\n");  // println!("{:?}", args.mode), main.rs:104 -- every rank prints it
+    std::fflush(stdout);
+    unsigned char id[EPI_COMM_ID_BYTES];
+    if (rank == 0 && !write_id_file(id_file)) return 1;
+    if (!read_id_file(id_file, id)) return 1;
+    const int n_dev = epi_device_count();
+    if (n_dev <= 0) { std::fprintf(stderr, "engine-app: no CUDA device (there is no CPU fallback)\n"); return 1; }
+    const int rc = epi_run_region(cfg, rank, world, id, a.seed, rank % n_dev, a.output_dir.c_str(), a.terminate_when_clear ? 1 : 0, nullptr, 0, nullptr, nullptr);
+    if (rc != EPI_OK) {
+        std::fprintf(stderr, "engine-app: rank %d: error %d: %s\n", rank, rc, epi_last_error(nullptr));
+        return 1;
+    }
+    return 0;
+}
+
+int run_mpi(const Args& a) {
     const std::string config_file = a.has_config ? a.config : "engine/config/simulation.json";  // main.rs:143-144
-    std::string exe = argv0;
-    const size_t slash = exe.rfind('/');
-    const std::string pkg_dir = slash == std::string::npos ? "." : exe.substr(0, slash);
-    const std::string root = pkg_dir + "/..";
-    const char* old = std::getenv("PYTHONPATH");
-    setenv("PYTHONPATH", old ? (root + ":" + old).c_str() : root.c_str(), 1);
-    std::vector<std::string> cmd = {"python", "-m", "epirust_b200.engine_app", "--launch", "-m", "mpi", "-c", config_file, "-o", a.output_dir,
-                                    "--seed", std::to_string(a.seed), "-t", std::to_string(a.threads)};
-    if (a.nproc > 0) { cmd.push_back("--nproc"); cmd.push_back(std::to_string(a.nproc)); }
-    std::vector<char*> av;
-    for (auto& s : cmd) av.push_back(const_cast<char*>(s.c_str()));
-    av.push_back(nullptr);
-    execvp(av[0], av.data());
-    std::perror("engine-app: cannot start the multi-region launcher (python)");
-    return 1;
+    epi_configuration* cfg = nullptr;
+    if (epi_configuration_read(config_file.c_str(), &cfg) != EPI_OK) {  // Configuration::read(..).expect + config.validate()
+        std::fprintf(stderr, "Error while reading config: %s\n", epi_last_error(nullptr));
+        return 1;
+    }
+    const int regions = epi_configuration_regions(cfg);
+    const char* env_rank = std::getenv("RANK");
+    const char* env_world = std::getenv("WORLD_SIZE");
+    if (env_rank && env_world) {
+        const int rank = std::atoi(env_rank), world = std::atoi(env_world);
+        if (world < 1 || world > regions || rank < 0 || rank >= world) {
+            std::fprintf(stderr, "engine-app: RANK=%d WORLD_SIZE=%d do not fit the %d regions of %s\n", rank, world, regions, config_file.c_str());
+            return 1;
+        }
+        const char* f = std::getenv("EPI_COMM_ID_FILE");
+        const char* port = std::getenv("MASTER_PORT");
+        const std::string id_file = f ? f : std::string("/tmp/epi_comm_") + (port ? port : "0") + ".id";
+        const int rc = run_rank(a, cfg, rank, world, id_file);
+        if (rank == 0) std::remove(id_file.c_str());
+        return rc;
+    }
+    const int world = a.nproc > 0 ? std::min(a.nproc, regions) : regions;
+    const std::string id_file = "/tmp/epi_comm_" + std::to_string((long)getpid()) + ".id";
+    std::remove(id_file.c_str());
+    std::vector<pid_t> kids;
+    for (int rank = 0; rank < world; ++rank) {
+        std::fflush(stdout);
+        std::fflush(stderr);
+        const pid_t pid = fork();  // before any CUDA call in this process: each child initialises CUDA for itself
+        if (pid < 0) { std::perror("engine-app: fork"); break; }
+        if (pid == 0) _exit(run_rank(a, cfg, rank, world, id_file));
+        kids.push_back(pid);
+    }
+    int failed = (int)kids.size() != world;
+    size_t left = kids.size();
+    while (left) {
+        int status = 0;
+        const pid_t pid = wait(&status);
+        if (pid < 0) break;
+        --left;
+        if (!(WIFEXITED(status) && WEXITSTATUS(status) == 0) && !failed) {
+            failed = 1;  // a rank died: the others would wait for it in the next collective
+            for (pid_t k : kids)
+                if (k != pid) kill(k, SIGTERM);
+        }
+    }
+    std::remove(id_file.c_str());
+    return failed;
 }
 
 }  // namespace
@@ -127,7 +215,7 @@ int main(int argc, char** argv) {
     Args a;
     const int pr = parse(argc, argv, a);
     if (pr) return pr == 1 ? 0 : 2;
-    if (a.mode == "mpi") return run_mpi(a, argv[0]);  // every region process prints its own mode line
+    if (a.mode == "mpi") return run_mpi(a);  // every region process prints its own mode line
     // println!("{:?}", args.mode) (main.rs:104)
     std::printf("%s\n", a.mode == "kafka" ? "Kafka" : "Standalone");
     std::fflush(stdout);

@@ -67,6 +67,7 @@ int settle_exchange(epi_engine* e) {
         CU(cudaStreamSynchronize(e->stream));
         CU(cudaGetLastError());
         const uint32_t err = e->h_tv->err;
+        if (err) e->pack_unsettled = e->unpack_unsettled = false;  // the exchange is abandoned (a pack that overflowed removed nobody)
         if (err & TERR_NO_SLOTS) return engine_fail(e, EPI_ERR_STATE, "region is out of agent slots: raise extra_capacity");
         if (err) return engine_fail(e, EPI_ERR_STATE, "traveller exchange: " + travel_error(err));
         if (!e->unpack_unsettled || e->h_tv->pending == 0) break;

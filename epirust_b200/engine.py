@@ -280,6 +280,37 @@ class Engine:
     def launch_count(self, reset=False):
         return int(self.L.epi_launch_count(self.h, int(reset)))
 
+    # ---- multi-region: the Transport behind the C ABI (include/epi.h "multi-region" block) ----
+    def comm_init(self, n_ranks, rank, unique_id):
+        """Join the NCCL communicator `unique_id` names (bytes from comm_unique_id()); rank == this engine's region."""
+        assert len(unique_id) == _ffi.COMM_ID_BYTES
+        buf = C.create_string_buffer(bytes(unique_id), _ffi.COMM_ID_BYTES)
+        self._check(self.L.epi_comm_init(self.h, n_ranks, rank, buf))
+
+    def comm_destroy(self):
+        self._check(self.L.epi_comm_destroy(self.h))
+
+    def exchange_kind(self, hour):
+        """TRAVEL_MIGRATE / TRAVEL_COMMUTE when `hour` is an exchange hour of the travel plan, else None."""
+        k = self.L.epi_exchange_kind(self.h, hour)
+        return None if k < 0 else k
+
+    def exchange(self, hour, kind):
+        """pack -> NCCL all-to-allv -> unpack on the engine's stream (deferred; finish_hour settles)."""
+        self._check(self.L.epi_exchange(self.h, hour, kind))
+
+    def count_outgoing(self, on=True):
+        self._check(self.L.epi_count_outgoing(self.h, int(on)))
+
+    def outgoing_travels(self):
+        """TravelCounter rows [n, 6]: hr, destination region index, susceptible, exposed, infected, recovered."""
+        n = C.c_uint32(0)
+        self._check(self.L.epi_outgoing_travels(self.h, None, 0, C.byref(n)))
+        out = np.zeros((n.value, 6), np.uint32)
+        if n.value:
+            self._check(self.L.epi_outgoing_travels(self.h, _ptr(out), n.value, C.byref(n)))
+        return out
+
     @property
     def device_bytes(self):
         return int(self.L.epi_device_bytes(self.h))
@@ -318,3 +349,132 @@ def run_standalone(cfg, seed=1, device=0, output_dir=None, engine_id="0"):
     if rc:
         raise EpiError(f"epi_run_standalone failed ({rc}): {L.epi_last_error(None).decode()}")
     return rows[: n.value].copy(), secs.value
+
+
+# ---- multi-region host driver over the C ABI ------------------------------------------------------------------------------
+def comm_unique_id():
+    """ncclGetUniqueId (epi_comm_unique_id): 128 bytes one rank creates and hands to the others."""
+    L = _ffi.load()
+    buf = C.create_string_buffer(_ffi.COMM_ID_BYTES)
+    if L.epi_comm_unique_id(buf):
+        raise EpiError(L.epi_last_error(None).decode())
+    return buf.raw
+
+
+def device_count():
+    return int(_ffi.load().epi_device_count())
+
+
+def travel_plan_struct(plan):
+    """dict(n_regions, migration=RxR or None, commute=RxR or None, start_migration_hour, end_migration_hour) -> (EpiTravelPlan, keep-alive arrays)"""
+    R = int(plan["n_regions"])
+    mig = np.ascontiguousarray(plan.get("migration") if plan.get("migration") is not None else np.zeros((R, R)), np.uint32)
+    com = np.ascontiguousarray(plan.get("commute") if plan.get("commute") is not None else np.zeros((R, R)), np.uint32)
+    tp = _ffi.EpiTravelPlan(R, int(plan.get("migration") is not None), int(plan.get("commute") is not None), mig.ctypes.data, com.ctypes.data,
+                            int(plan.get("start_migration_hour", 0)), int(plan.get("end_migration_hour", 0)))
+    return tp, (mig, com)
+
+
+def run_multi_hours(engines, first_hour, n_hours, terminate_when_clear=False):
+    """epi_run_multi_hours: Epidemiology::run_multi_engine's hour loop for the engines this process hosts (one with an NCCL
+    communicator, or every region of a local one).  Returns rows[n_local, n_rows, 7]; n_rows < n_hours when the termination rule fired."""
+    L = _ffi.load()
+    arr = (C.c_void_p * len(engines))(*[e.h for e in engines])
+    rows = np.zeros((len(engines), n_hours, 7), np.uint32)
+    n = C.c_uint32(0)
+    rc = L.epi_run_multi_hours(arr, len(engines), first_hour, n_hours, int(terminate_when_clear), _ptr(rows), C.byref(n))
+    if rc:
+        raise EpiError(f"error {rc}: {L.epi_last_error(engines[0].h).decode()}")
+    return rows[:, : n.value]
+
+
+def should_terminate(acks):
+    """TickAcks::should_terminate (orchestrator/src/ticks.rs:175-180) on Counts rows [n, 7]."""
+    a = np.ascontiguousarray(acks, np.uint32).reshape(-1, 7)
+    return bool(_ffi.load().epi_should_terminate(_ptr(a), len(a)))
+
+
+def multi_schedule_trace(plan, first_hour, n_hours, vaccinate_hours=(), unlock_hour=0):
+    """The order in which epi_run_multi_hours queues work for one region (host only): list of tuples
+    ("hours", first, n) / ("exchange_hour", h) / ("exchange", h, kind) / ("collect", [hours]) / ("finish", h)."""
+    L = _ffi.load()
+    tp, keep = travel_plan_struct(plan)
+    vac = np.ascontiguousarray(vaccinate_hours, np.uint32)
+    out = C.create_string_buffer(1 << 20)
+    if L.epi_multi_schedule_trace(C.byref(tp), _ptr(vac), len(vac), int(unlock_hour or 0), first_hour, n_hours, out, len(out)):
+        raise EpiError(L.epi_last_error(None).decode())
+    calls = []
+    for line in out.value.decode().splitlines():
+        w = line.split()
+        calls.append((w[0], [int(v) for v in w[1:]]) if w[0] == "collect" else (w[0], *[int(v) for v in w[1:]]))
+    return calls
+
+
+class Configuration:
+    """common::config::Configuration (configuration.rs:28-117) through epi_configuration_read: read + validate."""
+
+    def __init__(self, path):
+        self.L = _ffi.load()
+        h = C.c_void_p()
+        if self.L.epi_configuration_read(str(path).encode(), C.byref(h)):
+            raise EpiError(self.L.epi_last_error(None).decode())
+        self.h = h
+        self.n_regions = self.L.epi_configuration_regions(h)
+        self.regions = [self.L.epi_configuration_region_name(h, r).decode() for r in range(self.n_regions)]
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.epi_configuration_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def engine_config(self, region):
+        c = EpiConfig()
+        if self.L.epi_configuration_engine_config(self.h, region, C.byref(c)):
+            raise EpiError(self.L.epi_last_error(None).decode())
+        return c
+
+    def travel_plan(self, n_regions=None):
+        """The plan of the first n_regions regions as the dict Engine(plan=...) takes."""
+        R = n_regions or self.n_regions
+        tp = _ffi.EpiTravelPlan()
+        mig, com = np.zeros((R, R), np.uint32), np.zeros((R, R), np.uint32)
+        if self.L.epi_configuration_travel_plan(self.h, R, C.byref(tp), _ptr(mig), _ptr(com)):
+            raise EpiError(self.L.epi_last_error(None).decode())
+        return dict(n_regions=R, regions=self.regions[:R], migration=mig if tp.migration_enabled else None, commute=com if tp.commute_enabled else None,
+                    start_migration_hour=int(tp.start_migration_hour), end_migration_hour=int(tp.end_migration_hour))
+
+    def arrival_capacity(self, region):
+        return int(self.L.epi_configuration_arrival_capacity(self.h, region))
+
+    def run_region(self, region, n_ranks, unique_id, seed=1, device=0, output_dir=None, terminate_when_clear=False):
+        """One rank of `engine-app -m mpi` (epi_run_region).  Returns (rows[n, 7], hour-loop seconds)."""
+        hours = int(self.engine_config(region).hours)
+        rows = np.zeros((max(hours, 1), 7), np.uint32)
+        n, secs = C.c_uint32(0), C.c_double(0.0)
+        buf = C.create_string_buffer(bytes(unique_id), _ffi.COMM_ID_BYTES)
+        rc = self.L.epi_run_region(self.h, region, n_ranks, buf, seed, device, output_dir.encode() if output_dir else None, int(terminate_when_clear),
+                                   _ptr(rows), rows.shape[0], C.byref(n), C.byref(secs))
+        if rc:
+            raise EpiError(f"epi_run_region failed ({rc}): {self.L.epi_last_error(None).decode()}")
+        return rows[: n.value].copy(), secs.value
+
+
+def write_outputs(output_dir, engine_id, rows, events, travels=None, region_names=()):
+    """epi_write_outputs: the listeners' files (CSV, interventions JSON, optionally outgoing travels).  Returns the base path."""
+    L = _ffi.load()
+    rows = np.ascontiguousarray(rows, np.uint32).reshape(-1, 7)
+    ev = np.ascontiguousarray(events, np.int32).reshape(-1, 3)
+    tr = None if travels is None else np.ascontiguousarray(travels, np.uint32).reshape(-1, 6)
+    names = (C.c_char_p * max(1, len(region_names)))(*[n.encode() for n in region_names])
+    base = C.create_string_buffer(4096)
+    rc = L.epi_write_outputs(str(output_dir).encode(), engine_id.encode(), _ptr(rows), len(rows), _ptr(ev), len(ev), None if tr is None else _ptr(tr),
+                             0 if tr is None else len(tr), names, base, len(base))
+    if rc:
+        raise EpiError(L.epi_last_error(None).decode())
+    return base.value.decode()

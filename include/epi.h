@@ -340,6 +340,15 @@ uint32_t epi_configuration_arrival_capacity(const epi_configuration* c, int regi
 int epi_run_region(const epi_configuration* c, int region, int n_ranks, const void* unique_id, uint64_t seed, int device, const char* output_dir,
                    int terminate_when_clear, epi_counts* rows_out, uint32_t max_rows, uint32_t* n_rows, double* loop_seconds);
 
+/* Host only: what the listeners write at simulation_ended -- <output_dir>/output/simulation_<engine_id>_<UTC>.csv (CsvListener,
+ * listeners/csv_service.rs:44-71), ..._interventions.json (InterventionReporter, intervention_reporter.rs:28-63) and, when
+ * `travels` is not NULL, ..._outgoing_travels.csv (TravelCounter, travel_counter.rs:69-79; region_names[destination] names the
+ * regions).  base_out (may be NULL) receives the path without its suffix. */
+int epi_write_outputs(const char* output_dir, const char* engine_id, const epi_counts* rows, uint32_t n_rows, const epi_intervention_event* events,
+                      uint32_t n_events, const epi_outgoing_travel* travels, uint32_t n_travels, const char* const* region_names, char* base_out,
+                      uint64_t base_bytes);
+/* number of usable CUDA devices (0 when there is none; the library has no CPU fallback) */
+int epi_device_count(void);
 const char* epi_version(void);
 
 #ifdef __cplusplus

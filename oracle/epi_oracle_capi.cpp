@@ -294,6 +294,7 @@ int orc_multi_step(void* h, uint32_t hour, uint32_t* rows) {
 }
 uint32_t orc_multi_capacity(void* h, int r) { return ((MultiEngine*)h)->regions[(size_t)r].capacity; }
 uint32_t orc_multi_population(void* h, int r) { return ((MultiEngine*)h)->regions[(size_t)r].map.current_population(); }
+uint32_t orc_multi_max_place_rounds(void* h, int r) { return ((MultiEngine*)h)->regions[(size_t)r].max_place_rounds; }
 // state by slot (arrays of length capacity); absent slots read st = 7, everything else 0.  reg = home region | work region << 8
 int orc_multi_get_state(void* h, int r, int32_t* cx, int32_t* cy, uint32_t* st, uint32_t* t0, uint32_t* home, uint32_t* work, uint32_t* wsa, uint32_t* reg) {
     ORC_TRY

@@ -208,6 +208,7 @@ struct RegionEngine : Engine {
     // occupants and earlier rounds' winners count as occupied); of several proposals for one cell the lowest k wins; a
     // loser, or an arrival whose candidates were all occupied, tries again in the next round.
     static constexpr uint32_t PLACE_TRIES = 8;
+    uint32_t max_place_rounds = 0;  // most rounds one select_starting_points call needed so far (test hook: orc_multi_max_place_rounds)
     std::vector<Point> select_starting_points(const Area& area, size_t n, Hour hour) {
         std::vector<Point> out(n);
         std::vector<uint8_t> placed(n, 0);
@@ -241,6 +242,7 @@ struct RegionEngine : Engine {
                 const Citizen* win = round.get(prop[k]);
                 if (win && win->id == (uint32_t)k) { out[k] = prop[k]; placed[k] = 1; --left; Citizen m; taken.insert(prop[k], m); }
             }
+            max_place_rounds = std::max(max_place_rounds, attempt + 1u);
         }
         return out;
     }

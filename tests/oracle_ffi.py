@@ -273,6 +273,8 @@ def _multi_lib():
         L.orc_multi_capacity.argtypes = [C.c_void_p, C.c_int]
         L.orc_multi_population.restype = C.c_uint32
         L.orc_multi_population.argtypes = [C.c_void_p, C.c_int]
+        L.orc_multi_max_place_rounds.restype = C.c_uint32
+        L.orc_multi_max_place_rounds.argtypes = [C.c_void_p, C.c_int]
         L.orc_multi_get_state.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 8
         L.orc_multi_events.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         L.orc_kat_percent_outgoing.restype = C.c_double
@@ -315,6 +317,10 @@ class OracleMultiEngine:
 
     def population(self, r):
         return self.L.orc_multi_population(self.h, r)
+
+    def max_place_rounds(self, r):
+        """most placement rounds one arrival batch of region r needed so far (select_starting_points)"""
+        return self.L.orc_multi_max_place_rounds(self.h, r)
 
     def get_state(self, r):
         n = self.capacity(r)

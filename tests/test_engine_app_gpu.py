@@ -4,18 +4,18 @@ import glob
 import json
 import os
 import subprocess
-import sys
 
 import numpy as np
 import pytest
 
 import oracle_ffi as O
 from epirust_b200 import build as B
-from epirust_b200 import engine_app as A
+from epirust_b200.engine import Configuration, device_count
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
+INTERVENTION_NAMES = ("lockdown", "vaccination", "build_new_hospital")  # lockdown.rs:104-114, vaccination.rs:58-64, hospital.rs:78-84
 
 
 def read_rows(path):
@@ -37,39 +37,44 @@ def test_standalone_cli_writes_the_reference_outputs(tmp_path):
     assert (read_rows(csv_path) == rows_o).all()
     (js_path,) = glob.glob(str(tmp_path / "output" / "simulation_0_*_interventions.json"))
     ev = json.load(open(js_path))
-    assert [(e["hour"], e["intervention"]) for e in ev] == [(int(h), A.INTERVENTION_NAMES[int(k)]) for h, k, s in events_o]
+    assert [(e["hour"], e["intervention"]) for e in ev] == [(int(h), INTERVENTION_NAMES[int(k)]) for h, k, s in events_o]
 
 
-def test_two_region_cli_one_region_per_gpu(tmp_path):
-    """`engine-app -m mpi` with one process and one GPU per region (NCCL all-to-allv) against the multi-region oracle."""
-    import torch
-
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
-    cfg_path = os.path.join(GOLDEN, "two_regions_config.json")
-    env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""))
-    r = subprocess.run([sys.executable, "-m", "epirust_b200.engine_app", "--launch", "-m", "mpi", "-c", cfg_path, "-o", str(tmp_path), "--seed", "9"],
-                       capture_output=True, text=True, timeout=900, env=env, cwd=ROOT)
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
-    from epirust_b200.engine import config_from_json_string
-
-    engines, plan = A.read_configuration(cfg_path)
+def oracle_of(c, seed, hours):
     ocfgs = []
-    for e in engines:
-        g = config_from_json_string(json.dumps(e["config"]))
+    for r in range(c.n_regions):
+        g = c.engine_config(r)
         oc = O.EpiConfig()
         for name, _ in O.EpiConfig._fields_:
             v = getattr(g, name)
-            if hasattr(v, "__len__"):
+            if hasattr(v, "__len__") and not isinstance(v, (bytes, str)):
                 for i in range(len(v)):
                     getattr(oc, name)[i] = v[i]
             else:
                 setattr(oc, name, v)
         ocfgs.append(oc)
-    orc = O.OracleMultiEngine(ocfgs, seed=9, migration=plan["migration"], commute=plan["commute"], start_migration_hour=plan["start_migration_hour"],
-                              end_migration_hour=plan["end_migration_hour"], extra_capacity=2048, threads=2)
-    want = np.stack([orc.step(h) for h in range(1, 240)], axis=1)  # [region, hour, 7]
-    for k, name in enumerate(plan["regions"]):
+    plan = c.travel_plan()
+    extra = max(c.arrival_capacity(r) for r in range(c.n_regions))
+    orc = O.OracleMultiEngine(ocfgs, seed=seed, migration=plan["migration"], commute=plan["commute"], start_migration_hour=plan["start_migration_hour"],
+                              end_migration_hour=plan["end_migration_hour"], extra_capacity=extra, threads=2)
+    return np.stack([orc.step(h) for h in range(1, hours)], axis=1)  # [region, hour, 7]
+
+
+def test_two_region_cli_one_region_per_gpu(tmp_path):
+    """`engine-app -m mpi`: the binary forks one process per region, one region per GPU, NCCL all-to-allv between them --
+    with nothing but the binary on PATH (no Python, no torchrun) -- against the multi-region oracle."""
+    if device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    B.build()
+    cfg_path = os.path.join(GOLDEN, "two_regions_config.json")
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "PYTHONPATH")}
+    env["PATH"] = "/nonexistent"
+    r = subprocess.run([B.APP, "-m", "mpi", "-c", cfg_path, "-o", str(tmp_path), "--seed", "9"], capture_output=True, text=True, timeout=900, env=env, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert r.stdout.count("MPI\n") == 2
+    c = Configuration(cfg_path)
+    want = oracle_of(c, 9, 240)
+    for k, name in enumerate(c.regions):
         (p,) = glob.glob(str(tmp_path / "output" / f"simulation_{name}_*[0-9].csv"))
         got = read_rows(p)
         assert got.shape == want[k].shape and (got == want[k]).all(), f"region {name}: first differing hour {np.nonzero((got != want[k]).any(axis=1))[0][:3]}"
@@ -77,3 +82,34 @@ def test_two_region_cli_one_region_per_gpu(tmp_path):
         lines = open(t).read().splitlines()
         assert lines[0] == "hr,destination,susceptible,exposed,infected,recovered" and len(lines) > 1
         assert os.path.exists(p[:-4] + "_interventions.json")
+
+
+def test_two_ranks_through_the_c_abi_only():
+    """Two region processes that call nothing but epi_* (ctypes): epi_comm_unique_id -> epi_run_region on each rank."""
+    if device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import multiprocessing as mp
+
+    cfg_path = os.path.join(GOLDEN, "two_regions_config.json")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    from epirust_b200.engine import comm_unique_id
+
+    uid = comm_unique_id()
+    procs = [ctx.Process(target=_rank_main, args=(cfg_path, r, 2, uid, 9, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=600) for _ in procs)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    want = oracle_of(Configuration(cfg_path), 9, 240)
+    for r in range(2):
+        assert got[r].shape == want[r].shape and (got[r] == want[r]).all()
+
+
+def _rank_main(cfg_path, rank, world, uid, seed, q):
+    from epirust_b200.engine import Configuration as Cfg
+
+    rows, _ = Cfg(cfg_path).run_region(rank, world, uid, seed=seed, device=rank)
+    q.put((rank, rows))

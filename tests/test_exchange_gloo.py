@@ -1,10 +1,11 @@
-"""The N > 1 plumbing on CPU: world_size-2 gloo run of the padded all-to-all that carries the traveller records
-(epirust_b200.multi.DistExchange), with CPU tensors standing in for the device buffers."""
+"""The N > 1 plumbing on CPU, world_size-2 gloo: how the ranks of a torchrun-launched job (bench.py) meet -- rank 0's NCCL
+unique id reaches every rank (epirust_b200.multi.share_unique_id), timings are reduced as the maximum over ranks, every rank
+derives the same exchange schedule from the plan (epi_multi_schedule_trace: the real C++ hour loop with recording stand-ins)
+and, asked to join a communicator without a GPU, fails loudly with EPI_ERR_* instead of hanging or falling back."""
 import os
 import socket
 
 import numpy as np
-import torch
 import torch.multiprocessing as mp
 
 
@@ -19,38 +20,32 @@ def _free_port():
 def _worker(rank, world, port, ret):
     import torch.distributed as dist
 
-    from epirust_b200.multi import DistExchange, REC_WORDS
+    from epirust_b200 import _ffi
+    from epirust_b200.engine import multi_schedule_trace
+    from epirust_b200.multi import max_over_ranks, share_unique_id
 
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        x = DistExchange(torch.device("cpu"))
-        stride = 16
-        # rank r sends (r + 1) * (d + 2) records to rank d; header word 0 = count; record word 0 = sender, 1 = destination, 2 = index
-        counts = np.array([(rank + 1) * (d + 2) if d != rank else 0 for d in range(world)], np.int64)
-        send = torch.zeros((world, stride, REC_WORDS), dtype=torch.int32)
-        for d in range(world):
-            send[d, 0, 0] = int(counts[d])
-            for k in range(int(counts[d])):
-                send[d, 1 + k, :3] = torch.tensor([rank, d, k], dtype=torch.int32)
-        recv = x.exchange(send)
-        want_in = np.array([(s + 1) * (rank + 2) if s != rank else 0 for s in range(world)], np.int64)
-        ok = recv.shape == send.shape and recv[:, 0, 0].tolist() == want_in.tolist()
-        for s in range(world):
-            part = recv[s, 1:1 + int(want_in[s])]
-            ok = ok and bool((part[:, 0] == s).all()) and bool((part[:, 1] == rank).all()) and part[:, 2].tolist() == list(range(int(want_in[s])))
-        total = x.all_reduce_sum([int(counts.sum())])[0]
-        ok = ok and total == sum((r + 1) * (d + 2) for r in range(world) for d in range(world) if d != r)
-        # an exchange in which nobody travels still works (zero headers)
-        recv2 = x.exchange(torch.zeros((world, stride, REC_WORDS), dtype=torch.int32))
-        ok = ok and int(recv2[:, 0, 0].sum()) == 0
+        uid = share_unique_id(dist)
+        ids = [None] * world
+        dist.all_gather_object(ids, uid)
+        ok = len(uid) == _ffi.COMM_ID_BYTES and any(uid) and all(i == uid for i in ids)
+        ms = max_over_ranks(dist, [10.0 + rank, 5.0 - rank])
+        ok = ok and ms == [10.0 + world - 1, 5.0]
+        plan = dict(n_regions=world, migration=np.ones((world, world), np.uint32), commute=np.ones((world, world), np.uint32), start_migration_hour=48, end_migration_hour=336)
+        calls = multi_schedule_trace(plan, 1, 96)
+        mine = [c for c in calls if c[0] == "exchange"]
+        every = [None] * world
+        dist.all_gather_object(every, mine)
+        ok = ok and len(mine) == 2 * 4 + 2 and all(x == mine for x in every)  # 07:00 + 17:00 every day, midnight of days 3 and 4 (hours 72, 96)
         ret[rank] = bool(ok)
     finally:
         dist.destroy_process_group()
 
 
-def test_all_to_allv_of_traveller_records_world_size_2():
+def test_rendezvous_and_schedule_world_size_2():
     world = 2
     port = _free_port()
     mgr = mp.Manager()

@@ -41,7 +41,7 @@ def test_three_regions_commute_and_migration_bit_exact():
     engines, orc = build(R, kw, 31, plan, 600)
     try:
         assert_regions_equal(engines, orc, "init")
-        m = MultiRegion(engines, plan, stride_records=512)
+        m = MultiRegion(engines)
         hour = 1
         for day in range(7):
             rows = m.run(hour, 24)
@@ -63,7 +63,7 @@ def test_commute_only_hour_by_hour_state():
     plan = dict(n_regions=R, commute=np.array([[0, 120], [80, 0]], np.uint32))
     engines, orc = build(R, kw, 77, plan, 400)
     try:
-        m = MultiRegion(engines, plan, stride_records=512)
+        m = MultiRegion(engines)
         for hour in range(1, 24 * 3 + 1):
             rows = m.run(hour, 1)
             want = orc.step(hour)
@@ -88,7 +88,7 @@ def test_out_of_slots_is_an_error_not_a_crash():
     plan = dict(n_regions=R, commute=np.array([[0, 50], [0, 0]], np.uint32))
     engines, _ = build(R, kw, 5, plan, 10)
     try:
-        m = MultiRegion(engines, plan, stride_records=256)
+        m = MultiRegion(engines)
         with pytest.raises(EpiError, match="out of agent slots"):
             m.run(1, 8)
     finally:
@@ -96,7 +96,12 @@ def test_out_of_slots_is_an_error_not_a_crash():
             e.close()
 
 
-def test_segment_overflow_is_reported():
+def test_segment_overflow_is_reported_and_leaves_the_region_intact():
+    """epi_travel_pack into caller-owned segments that are too small: the error is reported and nobody was removed
+    (k_travel_pack used to vacate the leavers before the overflow was known)."""
+    import torch
+
+    from epirust_b200 import _ffi
     from epirust_b200.engine import EpiError
 
     R = 2
@@ -104,9 +109,45 @@ def test_segment_overflow_is_reported():
     plan = dict(n_regions=R, commute=np.array([[0, 50], [0, 0]], np.uint32))
     engines, _ = build(R, kw, 5, plan, 200)
     try:
-        m = MultiRegion(engines, plan, stride_records=16)  # 50 commuters do not fit a 15-record segment
+        e = engines[0]
+        for h in range(1, 8):
+            e.step(h)
+        before = e.get_state()
+        send = torch.zeros((R, 16, 8), dtype=torch.int32, device="cuda")  # 50 commuters do not fit a 15-record segment
         with pytest.raises(EpiError, match="stride_records"):
-            m.run(1, 8)
+            e.travel_pack(7, _ffi.TRAVEL_COMMUTE, send.data_ptr(), 16)
+        assert e.population == 2000
+        after = e.get_state()
+        for f in STATE_FIELDS:
+            assert (before[f] == after[f]).all(), f
+        assert int(send[:, 0, 0].sum()) == 0  # the headers promise no records
+        big = torch.zeros((R, 64, 8), dtype=torch.int32, device="cuda")
+        counts = e.travel_pack(7, _ffi.TRAVEL_COMMUTE, big.data_ptr(), 64)
+        assert counts.tolist() == [0, 50] and e.population == 1950
+    finally:
+        for e in engines:
+            e.close()
+
+
+def test_crowded_housing_needs_more_than_three_placement_rounds():
+    """select_starting_points (allocation_map.rs:339-347) in a housing strip that is ~97 % full at midnight: some arrival finds all
+    24 candidates of the first three rounds taken, so the host's settle loop (travel.cpp) must run further rounds."""
+    R = 2
+    kw = dict(n_agents=1420, grid_size=60, hours=200, exposed=20, pt=0.0, working=0.2)
+    plan = dict(n_regions=R, migration=np.array([[0, 15], [15, 0]], np.uint32), start_migration_hour=20, end_migration_hour=150)
+    engines, orc = build(R, kw, 3, plan, 1000)
+    try:
+        m = MultiRegion(engines)
+        hour = 1
+        for day in range(4):
+            rows = m.run(hour, 24)
+            for k in range(24):
+                want = orc.step(hour + k)
+                for r in range(R):
+                    assert (rows[r, k] == want[r]).all(), f"hour {hour + k} region {r}: gpu {rows[r, k]} oracle {want[r]}"
+            hour += 24
+            assert_regions_equal(engines, orc, f"end of day {day}")
+        assert max(orc.max_place_rounds(r) for r in range(R)) > 3
     finally:
         for e in engines:
             e.close()
@@ -120,7 +161,7 @@ def test_many_migrators_fill_houses_level_by_level():
     plan = dict(n_regions=R, migration=np.array([[0, 2500], [100, 0]], np.uint32), start_migration_hour=10, end_migration_hour=60)
     engines, orc = build(R, kw, 13, plan, 6000)
     try:
-        m = MultiRegion(engines, plan, stride_records=4096)
+        m = MultiRegion(engines)
         hour = 1
         for day in range(3):
             rows = m.run(hour, 24)
