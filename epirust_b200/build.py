@@ -16,7 +16,7 @@ CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libepirust_b200.so")
 APP = os.path.join(PKG, "engine-app")
 
-LIB_SOURCES = ["kernels.cu", "travel.cu", "engine.cpp", "host_model.cpp", "json.cpp", "simulation.cpp", "travel.cpp", "multi.cpp", "configuration.cpp"]
+LIB_SOURCES = ["kernels.cu", "tiles.cu", "travel.cu", "engine.cpp", "host_model.cpp", "json.cpp", "simulation.cpp", "travel.cpp", "multi.cpp", "configuration.cpp"]
 APP_SOURCES = ["engine_app_main.cpp"]
 
 NVCC_FLAGS = [

@@ -50,9 +50,10 @@ struct Timed {
     epi_engine* e;
     int kind;
     cudaEvent_t a = nullptr, b = nullptr;
-    Timed(epi_engine* e_, int kind_) : e(e_), kind(kind_) {
+    // hod: the hour of day of an hour / commit launch (per-hour-of-day sums, epi_get_hour_times), or -1
+    Timed(epi_engine* e_, int kind_, int hod = -1) : e(e_), kind(kind_ | ((hod + 1) << 8)) {
         e->launches++;
-        e->kernel_launches[kind]++;
+        e->kernel_launches[kind_]++;
         if (e->timing) {
             cudaEventCreate(&a);
             cudaEventCreate(&b);
@@ -72,7 +73,12 @@ void drain_events(epi_engine* e) {
         float ms = 0.f;
         cudaEventSynchronize(pe.second.second);
         cudaEventElapsedTime(&ms, pe.second.first, pe.second.second);
-        e->kernel_ms[pe.first] += ms;
+        e->kernel_ms[pe.first & 0xFF] += ms;
+        const int hod = (pe.first >> 8) - 1, kk = pe.first & 0xFF;
+        if (hod >= 0 && (kk == KK_HOUR || kk == KK_COMMIT)) {
+            e->hour_ms[hod * 2 + (kk == KK_COMMIT)] += ms;
+            e->hour_launches[hod * 2 + (kk == KK_COMMIT)]++;
+        }
         cudaEventDestroy(pe.second.first);
         cudaEventDestroy(pe.second.second);
     }
@@ -115,6 +121,88 @@ void drop_graph(epi_engine* e) {
     e->segment_graphs.clear();
 }
 
+// which tile order serves hour-of-day h: 0 = office tiles, 1 = house tiles, -1 = none (tiles.cu)
+int tile_order_of(uint32_t h) {
+    if ((h >= 9u && h <= 11u) || (h >= 13u && h <= 15u)) return 0;
+    if (h >= 18u && h <= 22u) return 1;
+    return -1;
+}
+
+TileGeom make_tile_geom(const epi_engine* e, int order) {
+    auto env_int = [](const char* name, int dflt) { const char* v = std::getenv(name); return v && *v ? std::max(1, std::atoi(v)) : dflt; };
+    TileGeom g{};
+    if (order == 0) {
+        g.ox = e->P.work.sx; g.oy = e->P.work.sy; g.unit = 10; g.units_x = e->P.office_nx; g.units_y = e->P.office_ny;
+        g.tile_units = env_int("EPI_TILE_OFFICES", 8);
+        g.cls = 1;  // RC_OFFICE
+        g.cap = (uint32_t)g.tile_units * 100u;
+        g.threads = (uint32_t)env_int("EPI_TILE_OFFICE_THREADS", 256);
+    } else {
+        g.ox = e->P.housing().sx; g.oy = e->P.housing().sy; g.unit = 2; g.units_x = e->P.house_nx; g.units_y = e->P.house_ny;
+        g.tile_units = env_int("EPI_TILE_HOUSES", 64);
+        g.cls = 0;  // RC_HOME
+        g.cap = (uint32_t)g.tile_units * 4u;
+        g.threads = (uint32_t)env_int("EPI_TILE_HOUSE_THREADS", 192);
+    }
+    g.threads = std::min(256u, (g.threads + 31u) / 32u * 32u);
+    g.chunks = (g.units_x + g.tile_units - 1) / g.tile_units;
+    g.n_tiles = (uint32_t)g.chunks * (uint32_t)g.units_y;
+    g.sp = 16 + ((g.unit * g.tile_units + 15 + 15) & ~15) + 16;
+    return g;
+}
+
+// (re)build the two tile orders from the agents' current home / work / work-status words
+int rebuild_tiles(epi_engine* e) {
+    e->tiles_ready = false;
+    if (!e->tiles_enabled) return EPI_OK;
+    drop_graph(e);
+    for (int o = 0; o < 2; ++o) {
+        cudaError_t r = build_tile_order(e->P, e->D, e->tile_geom[o], e->tile_ptrs[o], e->tile_keys_a, e->tile_keys_b, e->tile_ids, e->tile_temp, e->tile_temp_bytes, e->stream);
+        if (r != cudaSuccess) return engine_fail(e, EPI_ERR_CUDA, std::string("tile order: ") + cudaGetErrorString(r));
+        CU(cudaMemsetAsync(e->tile_ptrs[o].dirty, 0, (size_t)e->tile_geom[o].n_tiles * sizeof(uint32_t), e->stream));
+        e->launches += 2;
+    }
+    CU(cudaMemsetAsync(e->d_tile_misc, 0, 4 * sizeof(uint32_t), e->stream));
+    uint32_t first_generic[2] = {0, 0};
+    for (int o = 0; o < 2; ++o) CU(cudaMemcpyAsync(&first_generic[o], e->tile_ptrs[o].start + 2 * (size_t)e->tile_geom[o].n_tiles, sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    for (int o = 0; o < 2; ++o) e->tile_generic_bound[o] = e->P.n - first_generic[o];
+    e->tiles_ready = true;
+    return EPI_OK;
+}
+
+// Off unless asked for (EPI_TILES=1 / epi_set_tiles): bit-exact, but measured slower than the id-order kernels on B200 -- the
+// tile kernel saves ~45 % of the DRAM bytes of a plain hour and the commit pass of its members, and pays ~40 % more issue slots
+// per agent-hour (two window sources, warp-level settlement) in a kernel that was issue-bound to begin with (profiles/r02_tile_*).
+int setup_tiles(epi_engine* e, bool force) {
+    const char* v = std::getenv("EPI_TILES");
+    e->tiles_enabled = !e->multi && (force || (v && v[0] == '1'));
+    if (!e->tiles_enabled) return EPI_OK;
+    if (e->tile_temp) return EPI_OK;  // already allocated
+    const size_t n = e->P.n;
+    bool ok = true;
+    for (int o = 0; o < 2; ++o) {
+        e->tile_geom[o] = make_tile_geom(e, o);
+        if (e->tile_geom[o].n_tiles == 0 || tile_shared_bytes(e->tile_geom[o]) > 200u * 1024u) { e->tiles_enabled = false; return EPI_OK; }
+        ok &= dev_alloc(e, &e->tile_ptrs[o].perm, n) == cudaSuccess;
+        ok &= dev_alloc(e, &e->tile_ptrs[o].start, 2 * (size_t)e->tile_geom[o].n_tiles + 2) == cudaSuccess;
+        ok &= dev_alloc(e, &e->tile_ptrs[o].dirty, (size_t)e->tile_geom[o].n_tiles) == cudaSuccess;
+    }
+    ok &= dev_alloc(e, &e->tile_keys_a, n) == cudaSuccess;
+    ok &= dev_alloc(e, &e->tile_keys_b, n) == cudaSuccess;
+    ok &= dev_alloc(e, &e->tile_ids, n) == cudaSuccess;
+    ok &= dev_alloc(e, &e->d_tile_misc, 4) == cudaSuccess;
+    e->tile_temp_bytes = tile_sort_temp_bytes(e->P.n);
+    uint8_t* temp = nullptr;
+    ok &= dev_alloc(e, &temp, e->tile_temp_bytes) == cudaSuccess;
+    e->tile_temp = temp;
+    if (!ok) return engine_fail(e, EPI_ERR_CUDA, std::string("device allocation failed (tile orders): ") + cudaGetErrorString(cudaGetLastError()));
+    for (int o = 0; o < 2; ++o) { e->tile_ptrs[o].n_housing = e->d_tile_misc; e->tile_ptrs[o].misc = e->d_tile_misc; }
+    cudaError_t r = tiles_configure(e->tile_geom[0], e->tile_geom[1]);
+    if (r != cudaSuccess) return engine_fail(e, EPI_ERR_CUDA, std::string("tile kernels: ") + cudaGetErrorString(r));
+    return EPI_OK;
+}
+
 // enqueue one simulated hour (kernels only).  `inject`: draws table already on device.
 // prev_was_sleep: the previous hour of this same call was a sleep hour that already ran k_sleep -> nothing to do.
 int enqueue_hour(epi_engine* e, uint32_t hour, uint32_t hour_offset, bool inject, bool skip_sleep) {
@@ -130,13 +218,33 @@ int enqueue_hour(epi_engine* e, uint32_t hour, uint32_t hour_offset, bool inject
         Timed t(e, KK_SCAN);
         launch_hospital_scan(e->P, e->D, e->stream);
     }
+    const int order = (e->tiles_ready && !inject) ? tile_order_of(h) : -1;
+    if (order >= 0) {
+        // a plain movement hour: generic segment, then one CTA per office / house tile (tiles.cu); the commit pass only sees the
+        // proposals of the agents that took the global path
+        if (order == 1 && (h == 18u || hour_offset == 0)) {  // evening phase starts (or this batch starts inside it): who may step into any house?
+            Timed t(e, KK_MISC);
+            launch_count_housing(e->P, e->D, e->d_tile_misc, e->stream);
+        }
+        {
+            Timed t(e, KK_HOUR, (int)h);
+            e->launches += launch_hour_tiles(e->P, e->D, e->tile_geom[order], e->tile_ptrs[order], e->tile_generic_bound[order], hour_offset, e->stream) - 1u;
+        }
+        {
+            Timed t(e, KK_COMMIT, (int)h);
+            launch_commit(e->P, e->D, hour_offset, true, true, e->stream);
+        }
+        e->tile_hours++;
+        return EPI_OK;
+    }
     {
-        Timed t(e, KK_HOUR);
+        Timed t(e, KK_HOUR, (int)h);
         launch_hour(e->P, e->D, h, hour_offset, inject, e->stream);
     }
     {
-        Timed t(e, KK_COMMIT);
-        launch_commit(e->P, e->D, hour_offset, e->stream);
+        Timed t(e, KK_COMMIT, (int)h);
+        // the tile kernels rely on prop[] being all zero when their hour starts
+        launch_commit(e->P, e->D, hour_offset, false, e->tiles_ready && tile_order_of((h + 1u) % 24u) >= 0, e->stream);
     }
     return EPI_OK;
 }
@@ -164,7 +272,7 @@ int build_day_graph(epi_engine* e) {
     cudaGraph_t graph = nullptr;
     const bool timing = e->timing;
     e->timing = false;
-    const uint64_t launches0 = e->launches;
+    const uint64_t launches0 = e->launches, tile_hours0 = e->tile_hours;
     uint64_t kl0[EPI_N_KERNEL_KINDS];
     memcpy(kl0, e->kernel_launches, sizeof(kl0));
     CU(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
@@ -180,6 +288,7 @@ int build_day_graph(epi_engine* e) {
     e->timing = timing;
     e->day_graph_launches = (uint32_t)(e->launches - launches0);
     e->launches = launches0;
+    e->tile_hours = tile_hours0;
     memcpy(e->kernel_launches, kl0, sizeof(kl0));
     if (r != cudaSuccess) return engine_fail(e, EPI_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(r));
     r = cudaGraphInstantiate(&e->day_graph, graph, 0);
@@ -203,7 +312,7 @@ int segment_graph(epi_engine* e, uint32_t first_hour, uint32_t n, epi_engine::Se
         if (g.first == key) { *out = &g.second; return EPI_OK; }
     epi_engine::SegmentGraph sg;
     cudaGraph_t graph = nullptr;
-    const uint64_t launches0 = e->launches;
+    const uint64_t launches0 = e->launches, tile_hours0 = e->tile_hours;
     uint64_t kl0[EPI_N_KERNEL_KINDS];
     memcpy(kl0, e->kernel_launches, sizeof(kl0));
     CU(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
@@ -219,7 +328,9 @@ int segment_graph(epi_engine* e, uint32_t first_hour, uint32_t n, epi_engine::Se
     sg.n_sleep = (uint32_t)(e->kernel_launches[KK_SLEEP] - kl0[KK_SLEEP]);
     sg.n_active = (uint32_t)(e->kernel_launches[KK_HOUR] - kl0[KK_HOUR]);
     sg.n_scan = (uint32_t)(e->kernel_launches[KK_SCAN] - kl0[KK_SCAN]);
+    sg.n_tile = (uint32_t)(e->tile_hours - tile_hours0);
     e->launches = launches0;
+    e->tile_hours = tile_hours0;
     memcpy(e->kernel_launches, kl0, sizeof(kl0));
     if (r != cudaSuccess) return engine_fail(e, EPI_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(r));
     r = cudaGraphInstantiate(&sg.exec, graph, 0);
@@ -259,6 +370,7 @@ int queue_hours(epi_engine* e, uint32_t first_hour, uint32_t n, bool exchange_ho
             e->launches += sg->launches;
             e->kernel_launches[KK_SLEEP] += sg->n_sleep; e->kernel_launches[KK_HOUR] += sg->n_active; e->kernel_launches[KK_COMMIT] += sg->n_active;
             e->kernel_launches[KK_SCAN] += sg->n_scan;
+            e->tile_hours += sg->n_tile;
         }
         bool sleep_done = false;
         for (uint32_t k = 0; k < len; ++k) {
@@ -285,8 +397,11 @@ int collect_hours(epi_engine* e, std::vector<epi_counts>& rows) {
     const uint32_t n = (uint32_t)e->pend_kind.size();
     if (n == 0) return EPI_OK;
     CU(cudaMemcpyAsync(e->h_counts, e->D.counts, (size_t)n * 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+    e->h_small[63] = 0;
+    if (e->tiles_ready) CU(cudaMemcpyAsync(e->h_small + 63, e->d_tile_misc + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
     if (e->timing) drain_events(e);
+    if (e->h_small[63]) return engine_fail(e, EPI_ERR_STATE, "tile kernels: an agent's home / work word does not match its tile (stale tile order)");
     const std::vector<uint8_t> kind = e->pend_kind;
     const std::vector<uint32_t> population = e->pend_population;
     const uint32_t first_hour = e->pend_first;
@@ -344,6 +459,7 @@ int run_chunk(epi_engine* e, uint32_t first_hour, uint32_t n, bool inject, epi_c
             CU(cudaGraphLaunch(e->day_graph, e->stream));
             e->launches += e->day_graph_launches;
             e->kernel_launches[KK_SLEEP] += 1; e->kernel_launches[KK_HOUR] += 18; e->kernel_launches[KK_COMMIT] += 18; e->kernel_launches[KK_SCAN] += 1;
+            if (e->tiles_ready) e->tile_hours += 11;
             for (uint32_t k = 0; k < 24; ++k) { const uint32_t h = (hour + k) % 24u; ran[off + k] = !(h >= 2 && h <= 6); }
             off += 24;
             sleep_done = false;
@@ -359,8 +475,11 @@ int run_chunk(epi_engine* e, uint32_t first_hour, uint32_t n, bool inject, epi_c
     }
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(e->h_counts, e->D.counts, (size_t)n * 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+    e->h_small[63] = 0;
+    if (e->tiles_ready) CU(cudaMemcpyAsync(e->h_small + 63, e->d_tile_misc + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
     if (e->timing) drain_events(e);
+    if (e->h_small[63]) return engine_fail(e, EPI_ERR_STATE, "tile kernels: an agent's home / work word does not match its tile (stale tile order)");
     for (uint32_t k = 0; k < n; ++k) {
         if (ran[k]) {
             const epi_counts prev = e->last_counts;
@@ -656,6 +775,10 @@ int epi_create_multi(const epi_config* cfg_in, uint64_t seed, int device, int re
         rc = rebuild_grid(e);
         if (rc) return fail(rc);
         initial_counts(e);
+        rc = setup_tiles(e, false);
+        if (rc) return fail(rc);
+        rc = rebuild_tiles(e);
+        if (rc) return fail(rc);
     } catch (const std::exception& ex) {
         e->err = ex.what();
         return fail(EPI_ERR_CONFIG);
@@ -674,6 +797,9 @@ void epi_destroy(epi_engine* e) {
     void* ptrs[] = {e->D.cell, e->D.st, e->D.t0, e->D.home, e->D.work, e->D.wsa, e->D.prop, e->grid_alloc, e->D.claim, e->D.counts, e->D.tot,
                     e->d_clock, e->d_misc, e->d_draws, e->i_cell, e->i_st, e->i_t0, e->i_home, e->i_work, e->i_wsa, e->D.reg, e->i_reg};
     for (void* p : ptrs) if (p) cudaFree(p);
+    void* tile_ptrs[] = {e->tile_ptrs[0].perm, e->tile_ptrs[0].start, e->tile_ptrs[0].dirty, e->tile_ptrs[1].perm, e->tile_ptrs[1].start, e->tile_ptrs[1].dirty,
+                         e->tile_keys_a, e->tile_keys_b, e->tile_ids, e->d_tile_misc, e->tile_temp};
+    for (void* p : tile_ptrs) if (p) cudaFree(p);
     for (void* p : e->travel_allocs) cudaFree(p);
     if (e->h_tv) cudaFreeHost(e->h_tv);
     if (e->h_outgoing) cudaFreeHost(e->h_outgoing);
@@ -938,7 +1064,9 @@ int epi_set_state(epi_engine* e, uint32_t n, const int32_t* cx, const int32_t* c
     CU(cudaMemcpyAsync(&bad, e->d_misc + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
     if (bad) return engine_fail(e, EPI_ERR_ARG, "epi_set_state: " + std::to_string(bad) + " agents with a cell outside the grid or a house / office index out of range");
-    return rebuild_grid(e);
+    const int rc = rebuild_grid(e);
+    if (rc) return rc;
+    return rebuild_tiles(e);  // home / work / work status may have changed
 }
 
 int epi_get_regions(epi_engine* e, uint32_t* reg) {
@@ -982,6 +1110,7 @@ int epi_set_kernel_timing(epi_engine* e, int on) {
     drain_events(e);
     e->timing = on != 0;
     for (int k = 0; k < EPI_N_KERNEL_KINDS; ++k) { e->kernel_ms[k] = 0; e->kernel_launches[k] = 0; }
+    for (int k = 0; k < 48; ++k) { e->hour_ms[k] = 0; e->hour_launches[k] = 0; }
     return EPI_OK;
 }
 int epi_get_kernel_times(epi_engine* e, double* ms_total, uint64_t* launches) {
@@ -992,6 +1121,14 @@ int epi_get_kernel_times(epi_engine* e, double* ms_total, uint64_t* launches) {
     for (int k = 0; k < EPI_N_KERNEL_KINDS; ++k) { ms_total[k] = e->kernel_ms[k]; launches[k] = e->kernel_launches[k]; }
     return EPI_OK;
 }
+int epi_get_hour_times(epi_engine* e, double* ms_total, uint64_t* launches) {
+    if (!e || !ms_total || !launches) return engine_fail(e, EPI_ERR_ARG, "null argument");
+    CU(cudaSetDevice(e->device));
+    CU(cudaStreamSynchronize(e->stream));
+    drain_events(e);
+    for (int k = 0; k < 48; ++k) { ms_total[k] = e->hour_ms[k]; launches[k] = e->hour_launches[k]; }
+    return EPI_OK;
+}
 uint64_t epi_launch_count(const epi_engine* e, int reset) {
     if (!e) return 0;
     const uint64_t v = e->launches;
@@ -1000,5 +1137,27 @@ uint64_t epi_launch_count(const epi_engine* e, int reset) {
 }
 uint64_t epi_device_bytes(const epi_engine* e) { return e ? e->device_bytes : 0; }
 uint64_t epi_epoch_resets(const epi_engine* e) { return e ? e->epoch_resets : 0; }
+
+uint64_t epi_tile_hours(const epi_engine* e) { return e ? e->tile_hours : 0; }
+
+int epi_set_tiles(epi_engine* e, int on) {
+    if (!e) return engine_fail(e, EPI_ERR_ARG, "null engine");
+    CU(cudaSetDevice(e->device));
+    if (!on) {
+        if (e->tiles_ready) drop_graph(e);
+        e->tiles_ready = false;
+        e->tiles_enabled = false;
+        return EPI_OK;
+    }
+    if (e->multi) return engine_fail(e, EPI_ERR_STATE, "the tile kernels serve standalone engines");
+    if (e->tiles_ready) return EPI_OK;
+    {
+        const int rc = setup_tiles(e, true);
+        if (rc) return rc;
+    }
+    if (!e->tiles_enabled) return engine_fail(e, EPI_ERR_STATE, "the tile kernels cannot serve this geometry");
+    CU(cudaMemsetAsync(e->D.prop, 0, (size_t)e->P.n * sizeof(uint32_t), e->stream));  // the tile kernels start from all-zero proposals
+    return rebuild_tiles(e);
+}
 
 }  // extern "C"

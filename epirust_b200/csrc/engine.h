@@ -52,13 +52,25 @@ struct epi_engine {
     std::vector<uint32_t> pend_population;  // live agents when the hour was queued (allocation_map.rs:128 check at collect time)
     struct SegmentGraph {
         cudaGraphExec_t exec = nullptr;
-        uint32_t launches = 0, n_sleep = 0, n_active = 0, n_scan = 0;
+        uint32_t launches = 0, n_sleep = 0, n_active = 0, n_scan = 0, n_tile = 0;
     };
     std::vector<std::pair<uint32_t, SegmentGraph>> segment_graphs;  // key = (first hour of day) * 32 + hours (1..24)
+    // tile kernels of the plain movement hours (tiles.cu): [0] office tiles / order A (h = 9..11, 13..15), [1] house tiles / order B (h = 18..22)
+    bool tiles_enabled = false;  // standalone engines unless EPI_TILES=0
+    bool tiles_ready = false;    // the orders match the agents' home / work / work-status words
+    epi::TileGeom tile_geom[2]{};
+    epi::TilePtrs tile_ptrs[2]{};
+    uint32_t tile_generic_bound[2] = {0, 0};  // launch size of the generic segment (>= its length)
+    uint32_t *tile_keys_a = nullptr, *tile_keys_b = nullptr, *tile_ids = nullptr, *d_tile_misc = nullptr;
+    void* tile_temp = nullptr;
+    size_t tile_temp_bytes = 0;
+    uint64_t tile_hours = 0;  // hours that ran on the tile kernels (test hook: epi_tile_hours)
     // measurement
     bool timing = false;
     double kernel_ms[EPI_N_KERNEL_KINDS] = {0};
     uint64_t kernel_launches[EPI_N_KERNEL_KINDS] = {0};
+    double hour_ms[48] = {0};  // [hour of day][0 = hour kernels, 1 = commit]
+    uint64_t hour_launches[48] = {0};
     std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> pending_events;
     uint64_t launches = 0;
     // multi-region (Epidemiology::run_multi_engine): travel plan row of this region, host bookkeeping of the exchange

@@ -9,7 +9,15 @@ void launch_hospital_scan(const Params& P, const DevPtrs& D, cudaStream_t s);
 void launch_hour(const Params& P, const DevPtrs& D, uint32_t hour_of_day, uint32_t hour_offset, bool inject, cudaStream_t s);
 void launch_recount(const Params& P, const DevPtrs& D, cudaStream_t s);
 void launch_set_clock(Clock* clock, const Clock& value, cudaStream_t s);
-void launch_commit(const Params& P, const DevPtrs& D, uint32_t hour_offset, cudaStream_t s);
+void launch_commit(const Params& P, const DevPtrs& D, uint32_t hour_offset, bool lazy, bool zero_props, cudaStream_t s);
+// tiles.cu: the plain movement hours with the grid tiles and their claims in shared memory
+size_t tile_shared_bytes(const TileGeom& G);
+size_t tile_sort_temp_bytes(uint32_t n);
+cudaError_t build_tile_order(const Params& P, const DevPtrs& D, const TileGeom& G, const TilePtrs& TP, uint32_t* keys_a, uint32_t* keys_b, uint32_t* ids, void* temp,
+                             size_t temp_bytes, cudaStream_t s);
+void launch_count_housing(const Params& P, const DevPtrs& D, uint32_t* out, cudaStream_t s);
+unsigned launch_hour_tiles(const Params& P, const DevPtrs& D, const TileGeom& G, const TilePtrs& TP, uint32_t n_generic_bound, uint32_t hour_offset, cudaStream_t s);
+cudaError_t tiles_configure(const TileGeom& office, const TileGeom& house);
 void launch_sleep(const Params& P, const DevPtrs& D, uint32_t hour_offset, cudaStream_t s);
 void launch_lock(const Params& P, const DevPtrs& D, cudaStream_t s);
 void launch_unlock(const Params& P, const DevPtrs& D, cudaStream_t s);

@@ -166,6 +166,26 @@ struct TravelPtrs {
     const uint32_t* seg_cap;  // records (header included) the segment of each destination may hold, or nullptr = the stride
 };
 
+// ---- tile kernels of the plain movement hours (tiles.cu) ------------------------------------------------------------------------
+// A tile = up to tile_units x-adjacent units (10x10 offices / 2x2 houses) of one unit row; tile index = unit row * chunks + chunk.
+struct TileGeom {
+    int ox, oy;            // origin of unit (0, 0): the work strip's / housing strip's top-left cell
+    int unit;              // cells per unit side: OFFICE_SIZE = 10, HOME_SIZE = 2 (constants.rs:45-46)
+    int units_x, units_y;  // units per row, rows (area_factory, geography/area.rs:95-117)
+    int tile_units, chunks;  // units per tile along x; tiles per unit row
+    int cls;               // RC_OFFICE / RC_HOME (hour_common.cuh)
+    int sp;                // bytes per staged grid row in shared memory
+    uint32_t n_tiles, cap; // tiles; members a tile can settle on chip (more: the tile takes the global path)
+    uint32_t threads;      // CTA size of the tile kernel
+};
+struct TilePtrs {
+    uint32_t* perm;             // agent slots: tile 0's local members (ascending id), its riders, tile 1's, ..., then the generic segment
+    uint32_t* start;            // [2 * n_tiles + 2] start[2t] = tile t's local members, start[2t + 1] = its riders, start[2 * n_tiles] = the generic segment, then = slots
+    uint32_t* dirty;            // [n_tiles] set by the generic segment: somebody outside the tile proposes into it this hour
+    const uint32_t* n_housing;  // agents whose current_area is the housing strip (house tiles are off while it is non-zero)
+    uint32_t* misc;             // [0] = n_housing, [1] = "a tile order is stale" flag
+};
+
 struct Clock {           // device-resident so CUDA graphs can be replayed for any day
     uint32_t hour_base;  // kernels run hour = hour_base + offset
     uint32_t epoch_base; // claim stamp = hour - epoch_base + 1

@@ -277,6 +277,13 @@ class Engine:
         self._check(self.L.epi_get_kernel_times(self.h, _ptr(ms), _ptr(n)))
         return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(_ffi.KERNEL_KINDS)}
 
+    def hour_times(self):
+        """per hour of day: (ms of the hour's agent kernels, launches, ms of its commit pass, launches) -- needs set_kernel_timing(True)"""
+        ms = np.zeros(48, np.float64)
+        n = np.zeros(48, np.uint64)
+        self._check(self.L.epi_get_hour_times(self.h, _ptr(ms), _ptr(n)))
+        return {h: (float(ms[2 * h]), int(n[2 * h]), float(ms[2 * h + 1]), int(n[2 * h + 1])) for h in range(24) if n[2 * h] or n[2 * h + 1]}
+
     def launch_count(self, reset=False):
         return int(self.L.epi_launch_count(self.h, int(reset)))
 
@@ -310,6 +317,14 @@ class Engine:
         if n.value:
             self._check(self.L.epi_outgoing_travels(self.h, _ptr(out), n.value, C.byref(n)))
         return out
+
+    def set_tiles(self, on):
+        """tile kernels of the plain movement hours on / off (same results either way)"""
+        self._check(self.L.epi_set_tiles(self.h, int(on)))
+
+    @property
+    def tile_hours(self):
+        return int(self.L.epi_tile_hours(self.h))
 
     @property
     def device_bytes(self):

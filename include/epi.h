@@ -292,6 +292,9 @@ int epi_get_grid(epi_engine* e, uint8_t* out, uint64_t capacity, uint32_t* pitch
  * stream (this serialises nothing but adds event overhead; never on during the bench's headline timing). */
 int epi_set_kernel_timing(epi_engine* e, int on);
 int epi_get_kernel_times(epi_engine* e, double* ms_total, uint64_t* launches);
+/* the same per hour of day: [h * 2 + 0] the hour's agent kernels (one k_hour launch, or generic segment + tile kernel), [h * 2 + 1] its
+ * commit pass; 48 entries each */
+int epi_get_hour_times(epi_engine* e, double* ms_total, uint64_t* launches);
 /* number of kernel launches (graph kernel nodes included) since creation / last reset of the counter */
 uint64_t epi_launch_count(const epi_engine* e, int reset);
 /* device bytes held by the engine */
@@ -300,6 +303,13 @@ uint64_t epi_device_bytes(const epi_engine* e);
  * ceil(log2(agent slots))) were used up: 255 hours at 10 M agents.  epi_run_hours / epi_enqueue_hours split their work at
  * that limit.  (No reference equivalent: the reference clears its `upcoming` map every hour, allocation_map.rs:131-134.) */
 uint64_t epi_epoch_resets(const epi_engine* e);
+/* Optional tile kernels for the plain movement hours (h % 24 in 9..11, 13..15, 18..22) of a standalone engine (csrc/tiles.cu: one
+ * warp per run of adjacent offices / houses, the run's grid bytes staged into shared memory by TMA bulk copies, lowest-id claims
+ * settled on chip, no claim[] traffic and no commit pass for the members).  Same results bit for bit; off by default because the
+ * id-order kernels are faster on B200.  epi_set_tiles switches them on / off (environment EPI_TILES=1 = on at
+ * creation), epi_tile_hours counts the hours that took them.  (No reference equivalent.) */
+int epi_set_tiles(epi_engine* e, int on);
+uint64_t epi_tile_hours(const epi_engine* e);
 
 /* ---- host driver: the engine-app equivalent ----------------------------------------------------------------- */
 /* Parse the reference's simulation-config JSON (common::config::Config::read, common/src/config/mod.rs:124-128). */
