@@ -112,13 +112,17 @@ class ClockSampler:
 
 
 def measured_traffic(workload):
-    """DRAM bytes of one active-hour pass (k_hour + k_commit) from the committed ncu --set full capture, or None."""
+    """DRAM bytes (dram__bytes_read + dram__bytes_write) of one movement-hour pass (k_hour + k_commit, average over the 16 movement
+    hours of one simulated day) from the committed ncu capture of this build, or (None, why).  bench.py cannot read DRAM counters
+    itself; the capture is tools/gpu_round.sh -> tools/day.py --json -> profiles/traffic.json."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     try:
         t = json.load(open(p))
-        return float(t["pass_dram_bytes_per_launch"]) if t.get("workload") == workload else None
-    except Exception:
-        return None
+        if t.get("workload") != workload:
+            return None, "no ncu capture of this workload"
+        return float(t["movement_pass_dram_bytes_per_launch"]), t.get("source", "profiles/traffic.json")
+    except Exception as ex:  # noqa: BLE001
+        return None, f"profiles/traffic.json unreadable: {ex}"
 
 
 def algorithmic_bytes(n_agents, first_hour, n_hours):
@@ -128,48 +132,75 @@ def algorithmic_bytes(n_agents, first_hour, n_hours):
     return total
 
 
-def cpu_reference(wl, steps, warmup, budget_s=150.0, threads=None):
-    """The CPU restatement of the reference algorithm on a bounded sample.  Every step = the hours 6,7,8,9 of one
-    simulated day (1 sleep + 3 active hours = the 6:18 day mix) on the full population."""
+REFERENCE_SAMPLE_AGENTS = 1_000_000  # the CPU arm's region: same density and rules, population scaled so K + W whole days take minutes
+
+
+def reference_config(wl, hours):
+    """The workload's config for the CPU arm: the workload itself up to 1 M agents, else a 1 M-agent region of the same density
+    (rho = 0.16), starting infections and intervention thresholds scaled with the population."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_ffi as O
 
-    threads = threads or os.cpu_count() or 1
     kw = dict(WORKLOADS[wl])
-    cfg = O.make_config(hours=1080, **kw)
+    n = kw["n_agents"]
+    scale = 1.0
+    if n > REFERENCE_SAMPLE_AGENTS:
+        scale = REFERENCE_SAMPLE_AGENTS / n
+        kw.update(WORKLOADS["1m"])
+        src = WORKLOADS[wl]
+        kw["exposed"] = max(1, int(round(src["exposed"] * scale)))
+        if "lockdown" in src:
+            kw["lockdown"] = (max(1, int(round(src["lockdown"][0] * scale))), src["lockdown"][1])
+        if "hospital" in src:
+            kw["hospital"] = max(1, int(round(src["hospital"] * scale)))
+        if "vaccinate" in src:
+            kw["vaccinate"] = src["vaccinate"]
+    return O, O.make_config(hours=hours, **kw), kw["n_agents"], scale
+
+
+def cpu_reference(wl, steps, warmup, threads=None):
+    """The CPU restatement of the reference algorithm (oracle/, STREAM mode: hash map Point -> agent, OpenMP phase A, sequential
+    phase B, process_interventions after every hour -- the structure of engine/src/allocation_map.rs:67-134).  A step = ONE WHOLE
+    SIMULATED DAY, like the GPU arm; all `warmup` + `steps` days run."""
+    threads = threads or os.cpu_count() or 1
+    O, cfg, n, scale = reference_config(wl, 24 * (steps + warmup) + 1)
     t0 = time.time()
     eng = O.OracleEngine(cfg, seed=1, mode="stream", threads=threads)
     init_s = time.time() - t0
-    n = eng.population
-    per_step = []
-    done_hours = 0
-    t_begin = time.time()
-    for k in range(warmup + steps):
-        first = 24 * k + 6
-        s = eng.time_hours(first, 4)
-        if k >= warmup:
-            per_step.append(s)
-            done_hours += 4
-        if time.time() - t_begin > budget_s and len(per_step) >= 1:
-            break
+    per_day = []
+    for d in range(warmup + steps):
+        t = time.perf_counter()
+        for h in range(24 * d + 1, 24 * d + 25):
+            eng.step(h)
+        if d >= warmup:
+            per_day.append(time.perf_counter() - t)
     eng.close()
-    total = sum(per_step)
-    value = n * done_hours / total
-    sample = (f"{n} agents (full population of the workload), {len(per_step)} timed steps x simulated hours 6,7,8,9 of consecutive days "
-              f"(1 sleep + 3 active = the day's 6:18 mix), oracle STREAM mode (hash map, OpenMP phase A, sequential phase B), init {init_s:.1f}s excluded")
-    return value, threads, sample, total / max(1, len(per_step)), len(per_step)
+    total = sum(per_day)
+    value = n * 24.0 * len(per_day) / total
+    sample = (f"{n} agents" + (" (the workload's full population)" if scale == 1.0 else f" = a {scale:g} sub-sample region of the workload at the same density rho=0.16, "
+              "starting infections and intervention thresholds scaled alike") + f", {len(per_day)} timed steps of one whole simulated day (24 hours, interventions applied) after {warmup} "
+              f"warm-up days, oracle STREAM mode (hash map, OpenMP phase A, sequential phase B), init {init_s:.1f}s excluded")
+    return value, threads, sample, total / max(1, len(per_day)), len(per_day)
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    value, threads, sample, s_per_step, done = cpu_reference(args.workload, args.steps, min(args.warmup, 1))
+    K, W = args.steps, max(args.warmup, 3)
+    value, threads, sample, s_per_step, done = cpu_reference(args.workload, K, W)
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    cfg = {"workload": WORKLOAD_NAMES[args.workload], "agents": WORKLOADS[args.workload]["n_agents"], "grid_size": WORKLOADS[args.workload]["grid_size"],
+           "step": "one simulated day (24 hours)"}
+    if world > 1:  # BASELINE.md section 3: "#4/#5 one region on CPU, scaled by region count, flagged as such"
+        cfg["regions_timed"] = 1
+        cfg["scaled_by_region_count"] = world
+        value *= world
+        sample += f"; ONE region timed on the host cores, value = that x {world} regions (the regions are independent between exchanges; the traveller exchange is not in the CPU figure)"
     line = {
         "impl": "reference", "metric": "agent-steps/sec", "value": value, "unit": "agent-steps/s", "n_gpus": args.gpus, "steps": done,
-        "warmup": min(args.warmup, 1), "ms_per_step": s_per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u32", "data": "synthetic",
-        "config": {"workload": WORKLOAD_NAMES[args.workload], "agents": WORKLOADS[args.workload]["n_agents"], "grid_size": WORKLOADS[args.workload]["grid_size"]},
+        "warmup": W, "ms_per_step": s_per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u32", "data": "synthetic", "config": cfg,
         "cpu_baseline": {"value": value, "unit": "agent-steps/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -194,7 +225,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
 
-    from epirust_b200.engine import Engine, make_config, STATE_FIELDS, STATE_DTYPES
+    from epirust_b200.engine import Engine, make_config, STATE_FIELDS
     from epirust_b200.multi import MultiRegion, max_over_ranks, share_unique_id
 
     rank = int(os.environ.get("RANK", "0"))
@@ -207,10 +238,12 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     K, W = args.steps, max(args.warmup, 3)
     kw = dict(WORKLOADS[args.workload])
-    cfg = make_config(hours=24 * (K + W) + 1, **kw)
+    multi = world > 1
+    if multi and args.workload in ("2m", "20m") and rank != 0:
+        kw["exposed"] = 1  # the outbreak starts in engine1 only, the others get the default
+    cfg = make_config(hours=24 * (K + W) + 49, **kw)
     n = kw["n_agents"]
     stream = torch.cuda.Stream()
-    multi = world > 1
     plan = travel_plan_for(world, n) if multi else None
     eng = Engine(cfg, seed=1 + rank, device=local, region=rank if multi else 0, plan=plan, extra_capacity=max(32768, 2 * (world - 1) * (n // 1000 + n // 2000)) if multi else 0)
     eng.set_stream(stream.cuda_stream)
@@ -222,66 +255,95 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    def simulate(first_hour, n_hours, out):
+    def simulate(first_hour, n_hours):
         if not multi:
-            got, _ = eng.simulate_hours(first_hour, n_hours, out=out)
+            got, _ = eng.simulate_hours(first_hour, n_hours)
             return got
-        got = runner.run(first_hour, n_hours)[0]
-        out[: len(got)] = got
-        return got
+        return runner.run(first_hour, n_hours)[0]
 
     sampler = ClockSampler(local)
-    # ---------------- value: state resident in HBM ----------------
-    rows = np.zeros((24 * (K + W), 7), np.uint32)
+    # ---------------- value: state resident in HBM; one event per simulated day ----------------
     with torch.cuda.stream(stream):
         if multi:
             # the ranks' NCCL communicator lives behind the C ABI (epi_comm_init); torch.distributed only carries its unique id
             runner = MultiRegion([eng], n_ranks=world, rank=rank, unique_id=share_unique_id(dist, device=torch.device("cuda", local)))
-        simulate(1, 24 * W, rows)  # warm-up days (also builds the day graph)
+        simulate(1, 24 * W)  # warm-up days (also builds the day graph)
         barrier()
         if rank == 0:
             sampler.start()
         eng.launch_count(reset=True)
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+        rows = []
         t_wall0 = time.perf_counter()
-        ev0.record(stream)
-        got = simulate(24 * W + 1, 24 * K, rows[24 * W:])
-        ev1.record(stream)
+        for d in range(K):
+            ev[d].record(stream)
+            rows.append(simulate(24 * (W + d) + 1, 24))
+        ev[K].record(stream)
         barrier()
         t_wall1 = time.perf_counter()
-        ms = ev0.elapsed_time(ev1)
+        ms = ev[0].elapsed_time(ev[K])
+        day_ms = [ev[d].elapsed_time(ev[d + 1]) for d in range(K)]
         launches = eng.launch_count()
         clocks = sampler.stop() if rank == 0 else None
+    got = np.concatenate(rows)
     assert len(got) == 24 * K
     last_row = [int(v) for v in got[-1]]
     ms_max, wall_ms_max = max_over_ranks(dist, [ms, (t_wall1 - t_wall0) * 1e3], device="cuda") if world > 1 else (ms, (t_wall1 - t_wall0) * 1e3)
     value = world * n * 24.0 * K / (ms_max * 1e-3)
+    # which phase of the epidemic was timed: a locked-down city moves less (isolated agents skip the window load)
+    locked_days = []
+    events = eng.intervention_events()  # rows (hour, kind, status); kind 0 = lockdown, status 1 = locked down, 0 = revoked
+    for d in range(W, W + K):
+        locked = False
+        for hour, kind, status in events:
+            if kind == 0 and hour <= 24 * d:  # decided at the end of an earlier day's last hour
+                locked = bool(status)
+        locked_days.append(locked)
+    open_ms = [t for t, l in zip(day_ms, locked_days) if not l]
+    lock_ms = [t for t, l in zip(day_ms, locked_days) if l]
+    phase = {"timed_days": [W + 1, W + K], "locked_down_days": int(sum(locked_days)), "ms_per_day_open": (sum(open_ms) / len(open_ms)) if open_ms else None,
+             "ms_per_day_locked_down": (sum(lock_ms) / len(lock_ms)) if lock_ms else None, "infected_at_start": int(got[0][3]), "infected_at_end": int(got[-1][3])}
 
     # ---------------- per-kernel durations over the SAME simulated days (CUDA events around every launch, graphs off) ----
+    D_t = K
     if not multi:
         eng.reset()
         eng.simulate_hours(1, 24 * W)
         eng.set_kernel_timing(True)
         eng.simulate_hours(24 * W + 1, 24 * K)
     else:  # a multi-region engine cannot be rewound: time the next two days of the run
+        D_t = 2
         eng.set_kernel_timing(True)
         runner.run(24 * (W + K) + 1, 48)
     kt = eng.kernel_times()
+    ht = eng.hour_times()
     eng.set_kernel_timing(False)
-    hour_ms = kt["hour"][0] / max(1, kt["hour"][1])
-    commit_ms = kt["commit"][0] / max(1, kt["commit"][1])
-    sleep_ms = kt["sleep"][0] / max(1, kt["sleep"][1])
-    pass_ms = hour_ms + commit_ms
+    ev_total = sum(v[0] for v in kt.values()) / D_t  # every kernel of a day, event-timed (ms)
+    mov = sum(ht[h][0] + ht[h][2] for h in ht if 7 <= h <= 22) / D_t  # the 16 movement-hour passes of a day
+    act = sum(ht[h][0] + ht[h][2] for h in ht) / D_t  # + h = 23 and h = 0
+    # one timing source: the graph-replayed day (ms_per_step); the event-timed run only says how that day divides among the kernels
+    ms_day = ms / K
+    scale = ms_day / ev_total if ev_total > 0 else 1.0
+    mov_pass_ms, act_pass_ms = mov * scale / 16.0, act * scale / 18.0
     peak, peak_src = peaks()
-    achieved = ACTIVE_BYTES * n / (pass_ms * 1e-3) / 1e9
-    day_bytes = algorithmic_bytes(n, 24 * W + 1, 24 * K)
+    achieved = ACTIVE_BYTES * n / (mov_pass_ms * 1e-3) / 1e9
+    day_bytes = algorithmic_bytes(n, 24 * W + 1, 24)
+    traffic, traffic_src = measured_traffic(args.workload) if not multi else (None, "not captured for multi-region runs")
+    per_hour = {str(h): {"hour_ms": ht[h][0] / max(1, ht[h][1]), "commit_ms": ht[h][2] / max(1, ht[h][3])} for h in sorted(ht)}
     roofline = {
-        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": measured_traffic(args.workload) if not multi else None,
-        "kernel": "active-hour pass = k_hour (propose + transitions + counts + claim) + k_commit (lowest-id claim resolution)",
-        "algorithmic_bytes_per_launch": ACTIVE_BYTES * n, "avg_launch_ms": pass_ms, "peak_source": peak_src,
-        "per_kernel_ms": {"k_hour": hour_ms, "k_commit": commit_ms, "k_sleep": sleep_ms, "k_hospital_scan": kt["hospital_scan"][0] / max(1, kt["hospital_scan"][1]),
-                          "travel_kernels_total_ms": kt["travel"][0]},
-        "whole_run_achieved_gbs": day_bytes * world / (ms_max * 1e-3) / 1e9, "whole_run_frac": day_bytes / (ms_max * 1e-3) / 1e9 / peak,
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+        "kernel": "movement-hour pass (h%24 in 7..22) = k_hour (propose + transitions + counts + claim) + k_commit (lowest-id claim resolution); average of the 16 passes of a day",
+        "algorithmic_bytes_per_launch": ACTIVE_BYTES * n, "avg_launch_ms": mov_pass_ms, "peak_source": peak_src,
+        "timing_source": "ms_per_step (graph replay, CUDA events per simulated day) x the pass's share of the event-timed kernels of the same days (graphs off)",
+        "event_timed_day_ms": ev_total, "graph_replay_day_ms": ms_day,
+        "all_active_passes": {"passes": 18, "avg_launch_ms": act_pass_ms, "achieved": ACTIVE_BYTES * n / (act_pass_ms * 1e-3) / 1e9,
+                              "frac": ACTIVE_BYTES * n / (act_pass_ms * 1e-3) / 1e9 / peak,
+                              "note": "includes h=0 and h=23, whose kernels skip the grid for most agents (60 us passes credited with 82 B/agent)"},
+        "per_kernel_ms": {"k_hour": kt["hour"][0] / max(1, kt["hour"][1]), "k_commit": kt["commit"][0] / max(1, kt["commit"][1]), "k_sleep": kt["sleep"][0] / max(1, kt["sleep"][1]),
+                          "k_hospital_scan": kt["hospital_scan"][0] / max(1, kt["hospital_scan"][1]), "travel_kernels_per_day_ms": kt["travel"][0] / D_t},
+        "per_hour_of_day_ms": per_hour,
+        "whole_day": {"algorithmic_bytes": day_bytes, "achieved": day_bytes / (ms_max / K * 1e-3) / 1e9, "frac": day_bytes / (ms_max / K * 1e-3) / 1e9 / peak,
+                      "note": "18 active passes x 82 B + sleep hours x 8 B per agent over the whole simulated day (max over ranks for N > 1)"},
     }
 
     # ---------------- e2e: host buffers -> C ABI -> host rows ----------------
@@ -291,19 +353,16 @@ def run_ours(args):
         pinned = {f: torch.from_numpy(host_state[f]).pin_memory() for f in STATE_FIELDS}
         host_np = {f: pinned[f].numpy() for f in STATE_FIELDS}
         h2d = sum(host_np[f].nbytes for f in STATE_FIELDS)
-        rows2 = np.zeros((24 * (K + W), 7), np.uint32)
         barrier()
         t0 = time.perf_counter()
         eng.set_state(host_np)  # H2D of the whole population (cell, st, t0, home, work, wsa) + grid rebuild
-        got2, _ = eng.simulate_hours(1, 24 * K, out=rows2)  # Counts rows D2H every simulated day
+        eng.simulate_hours(1, 24 * K)  # Counts rows D2H every simulated day
         eng.sync()
         t1 = time.perf_counter()
-        e2e_s = torch.tensor([t1 - t0], dtype=torch.float64, device="cuda")
-        e2e_value = n * 24.0 * K / float(e2e_s.item())
-        e2e = {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": 24 * 28,
-               "note": "population uploaded from pinned host arrays once (amortised over the K days), 24 Counts rows read back per day"}
+        e2e = {"value": n * 24.0 * K / (t1 - t0), "unit": "agent-steps/s", "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": 24 * 28,
+               "note": "population uploaded from pinned host arrays once (amortised over the K days), 24 Counts rows read back per day; days 1..K of the run"}
     else:
-        # the same K days by the host's wall clock through the public multi-region API (epirust_b200.multi.MultiRegion.run)
+        # the same K days by the host's wall clock through the public multi-region API (epi_run_multi_hours)
         e2e = {"value": world * n * 24.0 * K / (wall_ms_max * 1e-3), "unit": "agent-steps/s", "h2d_bytes_per_step": 0,
                "d2h_bytes_per_step": 24 * 28 + 3 * (4 * (8 + world) + 4 * 32 * 8),
                "note": "host wall clock around the timed K days (max over ranks); the state stays in HBM (a region has no per-day host input), per day the 24 Counts rows come back and, per exchange, the exchange's scalars (TravelVars) and the running Counts totals; traveller records go GPU to GPU"}
@@ -313,13 +372,10 @@ def run_ours(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu_wl = args.workload if args.workload in ("1m", "2m") else "1m"
-        v, threads, sample, _, _ = cpu_reference(cpu_wl, 3, 1, budget_s=25.0)
-        if args.workload not in ("1m", "2m"):
-            sample = "SUB-SAMPLE at the same density rho=0.16: " + sample
+        v, threads, sample, _, _ = cpu_reference(args.workload, 3, 1)
         cpu = {"value": v, "unit": "agent-steps/s", "cores": threads, "kind": "port", "sample": sample}
         if threads > 4:  # the reference's default thread count (engine-app/src/main.rs:80 `-t 4`), SURVEY.md section 8d
-            v4, _, _, _, _ = cpu_reference(cpu_wl, 2, 1, budget_s=15.0, threads=4)
+            v4, _, _, _, _ = cpu_reference(args.workload, 2, 1, threads=4)
             cpu["at_reference_default_threads"] = {"value": v4, "cores": 4}
 
     if rank == 0:
@@ -332,7 +388,8 @@ def run_ours(args):
             "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": wl, "agents_per_gpu": n, "grid_size": kw["grid_size"], "step": "one simulated day (24 hours)",
                        "l2": "state + grids larger than L2 (no flush needed)" if n >= 5_000_000 else "working set fits the 126 MB L2; no flush (the real run is L2-resident too)",
-                       "regions": world, "exchange": "epi_exchange: pack -> grouped ncclSend/ncclRecv of the plan-bounded segments (count in the segment header) -> unpack, at h%24 in {0, 7, 17}" if multi else "n/a", "last_counts_row": last_row},
+                       "regions": world, "exchange": "epi_exchange: pack -> grouped ncclSend/ncclRecv of the plan-bounded segments (count in the segment header) -> unpack, at h%24 in {0, 7, 17}" if multi else "n/a",
+                       "phase": phase, "last_counts_row": last_row},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
