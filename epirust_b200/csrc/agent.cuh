@@ -27,4 +27,13 @@ __device__ __forceinline__ uint32_t count_category(uint32_t s) {
 }
 
 
+// debugging timeline (EPI_TRACE=1): one stamp = (tag << 56) | low 56 bits of the GPU's nanosecond timer
+__device__ __forceinline__ void trace_stamp(unsigned long long* trace, unsigned tag, unsigned hour) {
+    if (!trace) return;
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    const unsigned long long at = atomicAdd(trace, 2ull);
+    if (at + 2ull < (1ull << 16)) { trace[1 + at] = ((unsigned long long)tag << 56) | (t & ((1ull << 56) - 1ull)); trace[2 + at] = hour; }
+}
+
 }  // namespace epi

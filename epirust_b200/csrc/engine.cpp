@@ -344,7 +344,6 @@ int segment_graph(epi_engine* e, uint32_t first_hour, uint32_t n, epi_engine::Se
 // append hours [first, first + n) to the queue; exchange_hour: the single hour of an exchange (its kernels only)
 int queue_hours(epi_engine* e, uint32_t first_hour, uint32_t n, bool exchange_hour) {
     if (n == 0) return EPI_OK;
-    if (!e->pend_kind.empty() && e->pend_kind.back() == 2) return engine_fail(e, EPI_ERR_STATE, "an exchange hour is queued: epi_collect_hours / epi_finish_hour first");
     if (!e->pend_kind.empty() && first_hour != e->pend_first + (uint32_t)e->pend_kind.size())
         return engine_fail(e, EPI_ERR_STATE, "queued hours must be consecutive");
     if (e->pend_kind.size() + n > RING_ROWS) return engine_fail(e, EPI_ERR_STATE, "too many queued hours: call epi_collect_hours");
@@ -386,7 +385,6 @@ int queue_hours(epi_engine* e, uint32_t first_hour, uint32_t n, bool exchange_ho
         }
         off += len;
     }
-    e->have_last_row = e->have_last_row && !exchange_hour;
     CU(cudaGetLastError());
     return EPI_OK;
 }
@@ -408,10 +406,21 @@ int collect_hours(epi_engine* e, std::vector<epi_counts>& rows) {
     e->pend_kind.clear();
     e->pend_population.clear();
     for (uint32_t k = 0; k < n; ++k) {
-        if (kind[k] == 2) continue;
-        if (kind[k] == 1) {
+        const uint32_t* row = e->h_counts + (size_t)k * 8;
+        uint32_t pop = population[k];
+        if (kind[k] == 2) continue;  // an exchange hour driven by hand: its row comes from epi_finish_hour
+        if (kind[k] == 3) {
+            // an exchange hour: the device wrote its row after the arrivals were placed (k_travel_place), with the region's new
+            // population and the exchange's error flags next to it
+            const int rc = travel_status(e, row[7], row[6]);
+            if (rc) return rc;
+            e->pack_unsettled = e->unpack_unsettled = false;
+            pop = e->population;
+            row_to_counts(row, first_hour + k, &e->last_counts);
+            e->have_last_row = true;
+        } else if (kind[k] == 1) {
             const epi_counts prev = e->last_counts;
-            row_to_counts(e->h_counts + (size_t)k * 8, first_hour + k, &e->last_counts);
+            row_to_counts(row, first_hour + k, &e->last_counts);
             const uint32_t h = (first_hour + k) % 24u;
             if (h >= 1 && h <= 6 && e->have_last_row) {
                 const epi_counts& c = e->last_counts;
@@ -421,13 +430,13 @@ int collect_hours(epi_engine* e, std::vector<epi_counts>& rows) {
             }
             e->have_last_row = true;
         } else e->last_counts.hour = first_hour + k;
+        if (e->multi) pop = e->population;  // as of the last exchange row seen
         const epi_counts& c = e->last_counts;
         const uint64_t total = (uint64_t)c.susceptible + c.exposed + c.infected + c.hospitalized + c.recovered + c.deceased;
-        if (total != population[k])
-            return engine_fail(e, EPI_ERR_STATE, "counts total " + std::to_string(total) + " != population " + std::to_string(population[k]) + " at hour " + std::to_string(first_hour + k));
+        if (total != pop)
+            return engine_fail(e, EPI_ERR_STATE, "counts total " + std::to_string(total) + " != population " + std::to_string(pop) + " at hour " + std::to_string(first_hour + k));
         rows.push_back(c);
     }
-    if (kind.back() == 2) e->have_last_row = false;
     return EPI_OK;
 }
 
@@ -589,8 +598,21 @@ int alloc_travel(epi_engine* e, const epi_travel_plan* plan) {
     if ((rc = travel_alloc(e, &T.plan_house, 1))) return rc;
     if ((rc = travel_alloc(e, &T.plan_office, 1))) return rc;
     if ((rc = travel_alloc(e, &e->t_block_counts, (size_t)(e->P.n + 1023) / 1024 + 1 + ((size_t)(e->P.n + 1023) / 1024) * 32))) return rc;  // block counts | warp ballots
+    if ((rc = travel_alloc(e, &T.chunk_dest, ((size_t)T.list_cap / 256 + 2) * R))) return rc;
+    {
+        int sms = 0;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->device);
+        const size_t grid_most = (size_t)std::max(1, sms) * 8;  // k_travel_arrive never runs more blocks than this
+        if ((rc = travel_alloc(e, &T.hslice, 2 * (size_t)OFFICE_CAP * grid_most))) return rc;
+        if ((rc = travel_alloc(e, &T.tot_house, (size_t)TOT_COPIES * HOUSE_CAP))) return rc;
+        if ((rc = travel_alloc(e, &T.tot_office, (size_t)TOT_COPIES * OFFICE_CAP))) return rc;
+        if ((rc = travel_alloc(e, &T.foreign, ((size_t)(e->P.n + 1023) / 1024) * 32 + 32))) return rc;
+    }
     CU(cudaMallocHost((void**)&e->h_tv, sizeof(epi::TravelVars)));
     CU(cudaMemsetAsync(T.tv, 0, sizeof(epi::TravelVars), e->stream));
+    // the placement rounds' hash table starts empty and every round leaves it empty (k_travel_place)
+    CU(cudaMemsetAsync(T.table_keys, 0, (size_t)table * sizeof(uint32_t), e->stream));
+    CU(cudaMemsetAsync(T.table_vals, 0xFF, (size_t)table * sizeof(uint32_t), e->stream));
     CU(cudaMemcpyAsync(row, e->migration_row.data(), R * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
     CU(cudaStreamSynchronize(e->stream));
     return EPI_OK;
@@ -604,10 +626,23 @@ int reset_travel_state(epi_engine* e) {
     const uint32_t top = (uint32_t)e->free_stack0.size();
     CU(cudaMemsetAsync(e->T.tv, 0, sizeof(epi::TravelVars), e->stream));
     CU(cudaMemcpyAsync(&e->T.tv->free_top, &top, sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemcpyAsync(&e->T.tv->population, &e->population, sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
     CU(cudaMemcpyAsync(e->T.free_stack, e->free_stack0.data(), e->free_stack0.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
     CU(cudaMemcpyAsync(e->T.occ_house, e->occ_house0.data(), e->occ_house0.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
     CU(cudaMemcpyAsync(e->T.occ_office, e->occ_office0.data(), e->occ_office0.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
     CU(cudaStreamSynchronize(e->stream));
+    return EPI_OK;
+}
+
+// the running level histograms of the occupancy heaps and the foreign-slot marks, from the agents and occupancies now on the device
+int recount_travel(epi_engine* e) {
+    if (!e->multi) return EPI_OK;
+    CU(cudaMemsetAsync(e->T.tot_house, 0, (size_t)TOT_COPIES * HOUSE_CAP * sizeof(uint32_t), e->stream));
+    CU(cudaMemsetAsync(e->T.tot_office, 0, (size_t)TOT_COPIES * OFFICE_CAP * sizeof(uint32_t), e->stream));
+    CU(cudaMemsetAsync(e->T.foreign, 0, (((size_t)(e->P.n + 1023) / 1024) * 32 + 32) * sizeof(uint32_t), e->stream));
+    launch_travel_recount(e->P, e->D, e->T, e->geo.n_houses, e->geo.n_offices, e->stream);
+    e->launches += 3;
+    CU(cudaGetLastError());
     return EPI_OK;
 }
 
@@ -761,6 +796,11 @@ int epi_create_multi(const epi_config* cfg_in, uint64_t seed, int device, int re
         e->D.hosp_first = e->d_misc;
         e->D.clock = e->d_clock;
         e->D.draws = nullptr;
+        e->D.trace = nullptr;
+        if (std::getenv("EPI_TRACE")) {  // debugging timeline, read back with epi_debug_trace
+            ok = dev_alloc(e, &e->D.trace, (size_t)1 << 16) == cudaSuccess;
+            if (ok) cudaMemset(e->D.trace, 0, sizeof(unsigned long long) << 16);
+        }
         int rc = EPI_OK;
         if (plan) {
             rc = alloc_travel(e, plan);
@@ -773,6 +813,8 @@ int epi_create_multi(const epi_config* cfg_in, uint64_t seed, int device, int re
         rc = snapshot_initial(e);
         if (rc) return fail(rc);
         rc = rebuild_grid(e);
+        if (rc) return fail(rc);
+        rc = recount_travel(e);
         if (rc) return fail(rc);
         initial_counts(e);
         rc = setup_tiles(e, false);
@@ -795,7 +837,7 @@ void epi_destroy(epi_engine* e) {
     drop_graph(e);
     for (auto& pe : e->pending_events) { cudaEventDestroy(pe.second.first); cudaEventDestroy(pe.second.second); }
     void* ptrs[] = {e->D.cell, e->D.st, e->D.t0, e->D.home, e->D.work, e->D.wsa, e->D.prop, e->grid_alloc, e->D.claim, e->D.counts, e->D.tot,
-                    e->d_clock, e->d_misc, e->d_draws, e->i_cell, e->i_st, e->i_t0, e->i_home, e->i_work, e->i_wsa, e->D.reg, e->i_reg};
+                    e->d_clock, e->d_misc, e->d_draws, e->i_cell, e->i_st, e->i_t0, e->i_home, e->i_work, e->i_wsa, e->D.reg, e->i_reg, e->D.trace};
     for (void* p : ptrs) if (p) cudaFree(p);
     void* tile_ptrs[] = {e->tile_ptrs[0].perm, e->tile_ptrs[0].start, e->tile_ptrs[0].dirty, e->tile_ptrs[1].perm, e->tile_ptrs[1].start, e->tile_ptrs[1].dirty,
                          e->tile_keys_a, e->tile_keys_b, e->tile_ids, e->d_tile_misc, e->tile_temp};
@@ -860,6 +902,10 @@ int epi_reset(epi_engine* e) {
     e->events.clear();
     e->outgoing_travels.clear();
     e->outgoing_staged_hour = 0;
+    {
+        const int rc = recount_travel(e);
+        if (rc) return rc;
+    }
     return rebuild_grid(e);
 }
 
@@ -1139,6 +1185,22 @@ uint64_t epi_device_bytes(const epi_engine* e) { return e ? e->device_bytes : 0;
 uint64_t epi_epoch_resets(const epi_engine* e) { return e ? e->epoch_resets : 0; }
 
 uint64_t epi_tile_hours(const epi_engine* e) { return e ? e->tile_hours : 0; }
+
+int epi_debug_trace(epi_engine* e, uint64_t* out, uint64_t max_words, uint64_t* n_words) {
+    if (!e || !out || !n_words) return engine_fail(e, EPI_ERR_ARG, "null argument");
+    *n_words = 0;
+    if (!e->D.trace) return EPI_OK;
+    CU(cudaSetDevice(e->device));
+    CU(cudaStreamSynchronize(e->stream));
+    unsigned long long used = 0;
+    CU(cudaMemcpy(&used, e->D.trace, sizeof(used), cudaMemcpyDeviceToHost));
+    used = std::min<unsigned long long>(used, (1ull << 16) - 2ull);
+    used = std::min<unsigned long long>(used, max_words);
+    CU(cudaMemcpy(out, e->D.trace + 1, used * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    CU(cudaMemset(e->D.trace, 0, sizeof(unsigned long long)));
+    *n_words = used;
+    return EPI_OK;
+}
 
 int epi_set_tiles(epi_engine* e, int on) {
     if (!e) return engine_fail(e, EPI_ERR_ARG, "null engine");

@@ -91,9 +91,8 @@ struct epi_engine {
     // The reference's sequential bookkeeping of the exchange lives on the device (travel.cu): the free-slot stack (LIFO: arrivals
     // pop, departures push) and the house / office occupancy heaps (grid.rs:47-80, 279-341) as occupancy arrays in tie order.
     // The host keeps the stack height and the initial images for epi_reset.
-    bool pack_unsettled = false, unpack_unsettled = false;  // a deferred epi_travel_pack / unpack awaits its host-side settlement
-    epi::TravelArgs unpack_args{};
-    uint32_t unpack_attempt = 0, unpack_max_arrivals = 0;
+    bool pack_unsettled = false, unpack_unsettled = false;  // a deferred epi_travel_pack / unpack is in flight: the host's population mirror is stale
+    unsigned travel_blocks = 0, travel_blocks_small = 0;  // grids of the cooperative exchange kernels (4 / 1 blocks per SM)
     std::vector<uint32_t> free_stack0, occ_house0, occ_office0;
     uint32_t* i_reg = nullptr;
     epi::TravelPtrs T{};
@@ -113,4 +112,15 @@ namespace epi {
 constexpr uint32_t RING_ROWS = 2400;  // counts ring: up to 100 simulated days between host synchronisations
 int engine_fail(const epi_engine* e, int code, const std::string& msg);
 void set_global_error(const std::string& msg);
+int sync_travel(epi_engine* e);                                          // travel.cpp
+int travel_status(epi_engine* e, uint32_t err, uint32_t population);  // travel.cpp
+}  // namespace epi
+int epi_travel_unpack_impl(epi_engine* e, uint32_t hour, int kind, const void* recv_buf, uint64_t stride_records, uint32_t* counts_in, const uint32_t* wait_flags,
+                           uint32_t exchange_no);
+int epi_travel_pack_impl(epi_engine* e, uint32_t hour, int kind, void* send_buf, uint64_t stride_records, uint32_t* counts_out, epi::TravelRecord* const* peer_recv,
+                         uint32_t* const* peer_flags, uint32_t exchange_no);
+int epi_travel_exchange_fused(epi_engine* e, uint32_t hour, int kind, void* send_buf, const void* recv_buf, uint64_t stride_records, epi::TravelRecord* const* peer_recv,
+                              uint32_t* const* peer_flags, const uint32_t* wait_flags, uint32_t exchange_no);
+int epi_travel_unpack_wait(epi_engine* e, uint32_t hour, int kind, const void* recv_buf, uint64_t stride_records, const uint32_t* wait_flags, uint32_t exchange_no);
+namespace epi {
 }  // namespace epi

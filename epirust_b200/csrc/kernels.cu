@@ -103,6 +103,7 @@ template <bool LAZY>
 __global__ void __launch_bounds__(256) k_commit(Params P, DevPtrs D, uint32_t hour_offset, uint32_t zero_props) {
     const uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4u;
     const uint32_t hour = D.clock->hour_base + hour_offset;
+    if (blockIdx.x == 0 && threadIdx.x == 0) trace_stamp(D.trace, 1, hour);
     if (blockIdx.x == 0 && threadIdx.x < 32) {
         // the hour's Counts row = sum of the running totals' copies (all k_hour blocks of this hour have finished)
 #pragma unroll

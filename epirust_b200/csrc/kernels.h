@@ -24,12 +24,14 @@ void launch_unlock(const Params& P, const DevPtrs& D, cudaStream_t s);
 void launch_vaccinate(const Params& P, const DevPtrs& D, uint64_t thr, uint32_t hour, cudaStream_t s);
 void launch_import_state(const Params& P, const DevPtrs& D, const int32_t* cx, const int32_t* cy, uint32_t n_houses, uint32_t n_offices, uint32_t* bad, cudaStream_t s);
 void launch_build_grid(const Params& P, const DevPtrs& D, uint32_t* collisions, cudaStream_t s);
-// travel.cu (each returns the number of kernels it launched)
-unsigned launch_travel_leave(const Params& P, const DevPtrs& D, const TravelArgs& A, const TravelPtrs& T, uint32_t* block_counts, TravelRecord* send,
-                             uint32_t stride, cudaStream_t s);
-unsigned launch_travel_arrive(const Params& P, const DevPtrs& D, const TravelArgs& A, const TravelPtrs& T, const TravelRecord* recv, uint32_t stride,
-                              uint32_t max_arrivals, uint32_t n_houses, uint32_t n_offices, cudaStream_t s);
-unsigned launch_travel_rounds(const Params& P, const DevPtrs& D, const TravelArgs& A, const TravelPtrs& T, uint32_t max_arrivals, uint32_t first_attempt, uint32_t n_rounds,
-                              cudaStream_t s);
-void launch_travel_arrivals_done(const TravelPtrs& T, cudaStream_t s);
+// travel.cu: one cooperative launch each
+cudaError_t launch_travel_leave(const Params& P, const DevPtrs& D, const TravelArgs& A, const TravelPtrs& T, uint32_t* block_counts, TravelRecord* send,
+                                uint32_t stride, unsigned grid_blocks, TravelRecord* const* peer_recv, uint32_t* const* peer_flags, uint32_t exchange_no, cudaStream_t s);
+void launch_travel_recount(const Params& P, const DevPtrs& D, const TravelPtrs& T, uint32_t n_houses, uint32_t n_offices, cudaStream_t s);
+cudaError_t launch_travel_arrive(const Params& P, const DevPtrs& D, const TravelArgs& A, const TravelPtrs& T, const TravelRecord* recv, uint32_t stride,
+                                 uint32_t n_houses, uint32_t n_offices, unsigned grid_blocks, const uint32_t* wait_flags, uint32_t exchange_no, cudaStream_t s);
+cudaError_t launch_travel_exchange(const Params& P, const DevPtrs& D, const TravelArgs& A, const TravelPtrs& T, uint32_t* block_counts, TravelRecord* send, uint32_t stride,
+                                   const TravelRecord* recv, uint32_t n_houses, uint32_t n_offices, unsigned grid_blocks, TravelRecord* const* peer_recv,
+                                   uint32_t* const* peer_flags, const uint32_t* wait_flags, uint32_t exchange_no, cudaStream_t s);
+unsigned travel_grid_blocks(int device, int per_sm);
 }  // namespace epi

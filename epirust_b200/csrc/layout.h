@@ -119,7 +119,8 @@ enum : int { TRAVEL_MIGRATE = 0, TRAVEL_COMMUTE = 1 };
 struct TravelArgs {
     int kind;               // TRAVEL_MIGRATE (h % 24 == 0) or TRAVEL_COMMUTE (h % 24 in {7, 17})
     uint32_t hour, hour_of_day;
-    uint64_t thr_outgoing;  // Bernoulli threshold of EngineMigrationPlan::percent_outgoing
+    uint64_t thr_outgoing;  // Bernoulli threshold of EngineMigrationPlan::percent_outgoing (filled in on the device: it depends on the current population)
+    uint32_t row_index;     // counts ring row that receives the Counts of the exchange hour (k_travel_place), or 0xFFFFFFFF
 };
 
 // ---- traveller exchange: device-resident bookkeeping (travel.cu) ------------------------------------------------------------
@@ -128,9 +129,9 @@ constexpr uint32_t OCC_ABSENT = 0xFFFFFFFFu;  // a house / office that is not in
 constexpr uint32_t HOUSE_CAP = 4, OFFICE_CAP = 100;  // HOME_SIZE^2, OFFICE_SIZE^2 (constants.rs:45-46)
 enum : uint32_t {
     TERR_LIST_OVERFLOW = 1, TERR_SEGMENT_OVERFLOW = 2, TERR_NO_HOUSE = 4, TERR_NO_OFFICE = 8, TERR_HOUSES_FULL = 16, TERR_OFFICES_FULL = 32,
-    TERR_BAD_REGION = 64, TERR_NO_SLOTS = 128,
+    TERR_BAD_REGION = 64, TERR_NO_SLOTS = 128, TERR_PERCENT = 256, TERR_NO_PLACE = 512, TERR_PEER_TIMEOUT = 1024,
 };
-// scalars of one exchange; the host reads them back once per pack / unpack
+// scalars of the exchange; the host reads them when it collects Counts rows (errors are sticky)
 struct TravelVars {
     uint32_t total;      // leaving candidates, in ascending slot order
     uint32_t n_send;     // records written to the send buffer
@@ -142,6 +143,10 @@ struct TravelVars {
     uint32_t abort;      // err as k_travel_plan saw it: non-zero = this pack removes nobody
     uint32_t cnt[TRAVEL_MAX_REGIONS];   // records per destination region
     uint32_t base[TRAVEL_MAX_REGIONS];  // exclusive prefix of cnt
+    uint32_t hist[TRAVEL_MAX_REGIONS];  // commuters per destination while k_travel_leave counts them (zero between exchanges)
+    uint32_t population;  // live agents of the region (leavers subtracted by k_travel_leave, arrivals added by k_travel_arrive)
+    uint32_t rounds;      // most placement rounds one exchange needed so far (test hook)
+    uint32_t pend2[2];    // arrivals still without a cell after placement round a: pend2[a & 1]
 };
 // the pop sequence of an occupancy heap for K arrivals ("water filling"), see travel.cu
 struct FillPlan {
@@ -164,6 +169,10 @@ struct TravelPtrs {
     FillPlan *plan_house, *plan_office;
     int n_regions;
     const uint32_t* seg_cap;  // records (header included) the segment of each destination may hold, or nullptr = the stride
+    uint32_t* chunk_dest;     // [list_cap / 256 + 1][n_regions] commuters per destination in every chunk of 256 list entries
+    uint32_t* hslice;         // water filling scratch, per grid block of k_travel_arrive: [2][OFFICE_CAP][grid] slice totals
+    uint32_t *tot_house, *tot_office;  // areas per occupancy level overall, TOT_COPIES spread copies [copy][HOUSE_CAP] / [copy][OFFICE_CAP], kept current with bh_*
+    uint32_t* foreign;        // one bit per slot: the agent has its home or its work in another region (kept current by install / leave)
 };
 
 // ---- tile kernels of the plain movement hours (tiles.cu) ------------------------------------------------------------------------
@@ -203,6 +212,7 @@ struct DevPtrs {
     uint32_t* hosp_first;  // rank of the first vacant hospital cell in Area::iter order, or HOSP_NONE
     const Clock* clock;
     const uint64_t* draws; // injected draws table or nullptr
+    unsigned long long* trace;  // debugging (EPI_TRACE=1): globaltimer stamps, [0] = next free entry; entries = (tag << 56) | nanoseconds; or nullptr
 };
 
 }  // namespace epi

@@ -3,9 +3,11 @@
 // Reference: engine/src/transport/mod.rs:34-42, transport/mpi_transport.rs:44-215, epidemiology_simulation.rs:276-547,
 // orchestrator/src/ticks.rs:35-89,175-180.  C ABI: the "multi-region" block of include/epi.h.
 #include "multi.h"
+#include "kernels.h"
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 using namespace epi;
@@ -35,6 +37,11 @@ Comm::~Comm() {
         if (b.packed) cudaEventDestroy(b.packed);
         if (b.copied) cudaEventDestroy(b.copied);
     }
+    for (void* m : peer_mapped) cudaIpcCloseMemHandle(m);
+    if (recv2) cudaFree(recv2);
+    if (flags) cudaFree(flags);
+    if (d_peer_recv) cudaFree(d_peer_recv);
+    if (d_peer_flags) cudaFree(d_peer_flags);
     if (d_sum) cudaFree(d_sum);
     if (h_sum) cudaFreeHost(h_sum);
     if (nccl) ncclCommDestroy(nccl);
@@ -64,61 +71,58 @@ int run_multi_schedule(std::vector<RegionOps*>& regions, ExchangeOps& x, const P
     uint32_t hour = first_hour, last = first_hour + n_hours - 1u;
     std::vector<epi_counts> got;
     while (hour <= last) {
-        // the next exchange hour in [hour, last]
-        uint32_t xh = 0;
-        bool has_x = false;
-        for (uint32_t h = hour; h <= last && h < hour + 24u; ++h)
-            if (kind_of(h) >= 0) { xh = h; has_x = true; break; }
-        // The host waits for the device only where it has to look at Counts: after an exchange hour and at a decision hour of
-        // process_interventions (start of day, vaccination hour, unlock hour); with the termination rule also at a tick hour.
+        // The host waits for the device only where it has to look at Counts: at a decision hour of process_interventions (start of
+        // day, vaccination hour, unlock hour); with the termination rule also at a tick hour.  An exchange needs no wait: the
+        // counts, the population and the errors of the exchange stay on the device, and the exchange hour's Counts row reaches
+        // the counts ring like every other row.
         uint32_t decision = 0xFFFFFFFFu;
         for (RegionOps* r : regions) decision = std::min(decision, r->next_decision_hour(hour));
         if (terminate_when_clear)
             for (uint32_t h = hour; h <= last && h < hour + 24u; ++h)
                 if (tick(h)) { decision = std::min(decision, h); break; }
-        const uint32_t seg_end = std::min(std::min(last, decision), has_x ? xh - 1u : last);  // last plain hour queued in this round (may be hour - 1)
-        const bool has_seg = seg_end + 1u > hour;
-        if (has_seg)
-            for (RegionOps* r : regions) {
-                const int rc = r->enqueue_hours(hour, seg_end - hour + 1u);
+        const uint32_t seg_end = std::min(last, decision);  // last hour queued in this round
+        uint32_t h = hour;
+        while (h <= seg_end) {
+            uint32_t xh = h;
+            while (xh <= seg_end && kind_of(xh) < 0) ++xh;  // the next exchange hour of the round, or seg_end + 1
+            if (xh > h)
+                for (RegionOps* r : regions) {
+                    const int rc = r->enqueue_hours(h, xh - h);
+                    if (rc) return rc;
+                }
+            if (xh <= seg_end) {
+                for (RegionOps* r : regions) {
+                    const int rc = r->enqueue_hour(xh);
+                    if (rc) return rc;
+                }
+                const int rc = x.exchange(xh, kind_of(xh));
                 if (rc) return rc;
             }
-        const bool exchange_now = has_x && xh == seg_end + 1u && !(has_seg && seg_end == decision);
-        if (exchange_now) {
-            for (RegionOps* r : regions) {
-                const int rc = r->enqueue_hour(xh);
-                if (rc) return rc;
-            }
-            const int rc = x.exchange(xh, kind_of(xh));
-            if (rc) return rc;
+            h = xh + 1u;
         }
-        const uint32_t done = exchange_now ? xh : seg_end;
         unsigned long long active = 0;
         for (size_t i = 0; i < regions.size(); ++i) {
-            int rc = regions[i]->collect(got);
+            const int rc = regions[i]->collect(got);
             if (rc) return rc;
+            if (got.size() != seg_end - hour + 1u) return EPI_ERR_STATE;
             epi_counts* out = rows_out + i * (size_t)n_hours + (hour - first_hour);
             for (size_t k = 0; k < got.size(); ++k) out[k] = got[k];
-            if (exchange_now) {
-                rc = regions[i]->finish(xh, rows_out + i * (size_t)n_hours + (xh - first_hour));
-                if (rc) return rc;
-            }
-            const epi_counts& c = rows_out[i * (size_t)n_hours + (done - first_hour)];
+            const epi_counts& c = got.back();
             active += (unsigned long long)c.exposed + c.infected + c.hospitalized;
         }
-        if (terminate_when_clear && tick(done)) {
+        if (terminate_when_clear && tick(seg_end)) {
             // TickAcks::should_terminate (ticks.rs:175-180): the NEXT tick carries terminate = true and the engines break before
             // simulating its hour (epidemiology_simulation.rs:336-349)
             unsigned long long total = 0;
             const int rc = x.all_reduce_sum(active, &total);
             if (rc) return rc;
             if (total == 0) {
-                uint32_t t = done + 1u;
+                uint32_t t = seg_end + 1u;
                 while (t <= last && !tick(t)) ++t;
                 if (t <= last) last = t - 1u;
             }
         }
-        hour = done + 1u;
+        hour = seg_end + 1u;
     }
     *n_rows = last - first_hour + 1u;
     return EPI_OK;
@@ -178,6 +182,62 @@ int alloc_region_buffers(epi_engine* e, Comm& c, RegionBuffers& b) {
     return EPI_OK;
 }
 
+// Peer transport: exchange CUDA IPC handles of the receive areas and flag words through the communicator, map every peer's.
+// When the ranks cannot reach each other's memory (no peer access between the devices) peer_ok stays false on every rank and the
+// exchange uses ncclSend / ncclRecv.
+int setup_peer_transport(epi_engine* e, Comm& c) {
+    const size_t R = (size_t)c.n, me = (size_t)c.rank;
+    CU(cudaSetDevice(e->device));
+    CU(cudaMalloc((void**)&c.recv2, 2 * R * c.stride * sizeof(TravelRecord)));
+    CU(cudaMalloc((void**)&c.flags, R * sizeof(uint32_t)));
+    CU(cudaMemset(c.recv2, 0, 2 * R * c.stride * sizeof(TravelRecord)));
+    CU(cudaMemset(c.flags, 0, R * sizeof(uint32_t)));
+    struct Card { cudaIpcMemHandle_t recv, flags; int device; int ok; };
+    static_assert(sizeof(Card) % 4 == 0, "Card is sent as words");
+    Card mine{};
+    mine.device = e->device;
+    mine.ok = cudaIpcGetMemHandle(&mine.recv, c.recv2) == cudaSuccess && cudaIpcGetMemHandle(&mine.flags, c.flags) == cudaSuccess;
+    cudaGetLastError();
+    Card* d_cards = nullptr;
+    CU(cudaMalloc((void**)&d_cards, R * sizeof(Card)));
+    CU(cudaMemcpyAsync(d_cards + me, &mine, sizeof(Card), cudaMemcpyHostToDevice, e->stream));
+    NC(ncclAllGather(d_cards + me, d_cards, sizeof(Card), ncclChar, c.nccl, e->stream));
+    std::vector<Card> cards(R);
+    CU(cudaMemcpyAsync(cards.data(), d_cards, R * sizeof(Card), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    cudaFree(d_cards);
+    std::vector<TravelRecord*> peer_recv(R, nullptr);
+    std::vector<uint32_t*> peer_flags(R, nullptr);
+    int ok = 1;
+    for (size_t p = 0; p < R; ++p) ok = ok && cards[p].ok;
+    for (size_t p = 0; p < R && ok; ++p) {
+        if (p == me) { peer_recv[p] = c.recv2; peer_flags[p] = c.flags; continue; }
+        void *r = nullptr, *f = nullptr;
+        if (cudaIpcOpenMemHandle(&r, cards[p].recv, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; break; }
+        c.peer_mapped.push_back(r);
+        if (cudaIpcOpenMemHandle(&f, cards[p].flags, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; break; }
+        c.peer_mapped.push_back(f);
+        peer_recv[p] = (TravelRecord*)r;
+        peer_flags[p] = (uint32_t*)f;
+    }
+    cudaGetLastError();
+    // all ranks take the same path: one that could not map a peer sends everybody back to NCCL
+    int* d_ok = nullptr;
+    CU(cudaMalloc((void**)&d_ok, sizeof(int)));
+    CU(cudaMemcpyAsync(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    NC(ncclAllReduce(d_ok, d_ok, 1, ncclInt, ncclMin, c.nccl, e->stream));
+    CU(cudaMemcpyAsync(&ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    cudaFree(d_ok);
+    if (!ok) return EPI_OK;
+    CU(cudaMalloc((void**)&c.d_peer_recv, R * sizeof(TravelRecord*)));
+    CU(cudaMalloc((void**)&c.d_peer_flags, R * sizeof(uint32_t*)));
+    CU(cudaMemcpy(c.d_peer_recv, peer_recv.data(), R * sizeof(TravelRecord*), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c.d_peer_flags, peer_flags.data(), R * sizeof(uint32_t*), cudaMemcpyHostToDevice));
+    c.peer_ok = true;
+    return EPI_OK;
+}
+
 int pack_deferred(epi_engine* e, Comm& c, RegionBuffers& b, uint32_t hour, int kind) {
     e->T.seg_cap = b.d_caps[kind];
     const int rc = epi_travel_pack(e, hour, kind, b.send, c.stride, nullptr);
@@ -232,12 +292,27 @@ int nccl_exchange(epi_engine* e, uint32_t hour, int kind) {
     RegionBuffers& b = c.buffers[0];
     const size_t R = (size_t)c.n, me = (size_t)c.rank;
     CU(cudaSetDevice(e->device));
+    if (c.peer_ok) {
+        // every destination's segment goes straight into that rank's receive area over NVLink (the tail of the leave kernel); the
+        // receiver's arrive kernel waits for our flag
+        const uint32_t no = ++c.exchange_no;
+        e->T.seg_cap = b.d_caps[kind];
+        const int rc = epi_travel_exchange_fused(e, hour, kind, b.send, c.recv2 + (size_t)(no & 1u) * R * c.stride, c.stride, c.d_peer_recv, c.d_peer_flags, c.flags, no);
+        e->T.seg_cap = nullptr;
+        if (rc) return rc;
+        return stage_outgoing(e, c, b, hour, kind);
+    }
     int rc = pack_deferred(e, c, b, hour, kind);
     if (rc) return rc;
     rc = stage_outgoing(e, c, b, hour, kind);
     if (rc) return rc;
     // all-to-allv: segment p of the send buffer -> rank p, segment p of the receive buffer <- rank p; only the records the plan
     // can produce for the pair travel (the header carries the actual count)
+    static const bool skip_nccl = std::getenv("EPI_DEBUG_NO_NCCL") != nullptr;  // timing experiments only: nobody arrives
+    if (skip_nccl) {
+        CU(cudaMemsetAsync(b.recv, 0, R * c.stride * sizeof(TravelRecord), e->stream));
+        return epi_travel_unpack(e, hour, kind, b.recv, c.stride, nullptr);
+    }
     NC(ncclGroupStart());
     for (size_t p = 0; p < R; ++p) {
         if (p == me) continue;
@@ -296,11 +371,6 @@ struct EngineOps : RegionOps {
             for (const epi_counts& c : rows) note_outgoing(e, c.hour);
         return rc;
     }
-    int finish(uint32_t hour, epi_counts* row) override {
-        const int rc = epi_finish_hour(e, hour, row);
-        if (!rc) note_outgoing(e, hour);
-        return rc;
-    }
 };
 
 struct CommExchange : ExchangeOps {
@@ -343,6 +413,7 @@ struct TraceRegion : RegionOps {
     }
     int enqueue_hour(uint32_t hour) override {
         out += "exchange_hour " + std::to_string(hour) + "\n";
+        queued.push_back(hour);
         return EPI_OK;
     }
     int collect(std::vector<epi_counts>& rows) override {
@@ -354,11 +425,6 @@ struct TraceRegion : RegionOps {
         }
         out += "\n";
         queued.clear();
-        return EPI_OK;
-    }
-    int finish(uint32_t hour, epi_counts* row) override {
-        out += "finish " + std::to_string(hour) + "\n";
-        *row = epi_counts{hour, 1, 0, 0, 0, 0, 0};
         return EPI_OK;
     }
 };
@@ -409,6 +475,10 @@ int epi_comm_init(epi_engine* e, int n_ranks, int rank, const void* unique_id) {
     std::memcpy(&id, unique_id, sizeof(id));
     NC(ncclCommInitRank(&c->nccl, n_ranks, id, rank));
     e->comm = c;
+    if (!std::getenv("EPI_NO_PEER")) {
+        rc = setup_peer_transport(e, *c);
+        if (rc) { e->comm.reset(); return rc; }
+    }
     return EPI_OK;
 }
 

@@ -29,6 +29,17 @@ struct Comm {
     std::vector<epi_engine*> engines;      // local transport: all regions, by region index; nccl: the one engine
     std::vector<RegionBuffers> buffers;    // parallel to `engines`
     unsigned long long *d_sum = nullptr, *h_sum = nullptr;  // termination rule: all-reduce of exposed + infected + hospitalized
+    // Peer transport (one process per region, NVLink / NVSwitch peer memory): every rank exposes a double-buffered receive area and
+    // a flag word per source through CUDA IPC; a sender writes its segment straight into the destination's memory and then raises
+    // its flag there; the receiver's arrive kernel waits for the flags.  NCCL only carried the IPC handles (and the termination
+    // rule's all-reduce).  peer_ok == false: the ncclSend / ncclRecv path.
+    bool peer_ok = false;
+    TravelRecord* recv2 = nullptr;             // [2][n][stride] this rank's receive area (buffer = exchange number & 1)
+    uint32_t* flags = nullptr;                 // [n] flags[q] = number of the last exchange whose segment from rank q is complete
+    std::vector<void*> peer_mapped;            // what cudaIpcOpenMemHandle returned (closed by ~Comm)
+    TravelRecord** d_peer_recv = nullptr;      // device array [n]: rank p's recv2 as seen from here
+    uint32_t** d_peer_flags = nullptr;         // device array [n]: rank p's flags as seen from here
+    uint32_t exchange_no = 0;                  // exchanges done
     ~Comm();
 };
 
@@ -43,8 +54,7 @@ struct RegionOps {
     virtual uint32_t next_decision_hour(uint32_t hour) = 0;
     virtual int enqueue_hours(uint32_t first_hour, uint32_t n) = 0;
     virtual int enqueue_hour(uint32_t hour) = 0;
-    virtual int collect(std::vector<epi_counts>& rows) = 0;
-    virtual int finish(uint32_t hour, epi_counts* row) = 0;
+    virtual int collect(std::vector<epi_counts>& rows) = 0;  // waits; the rows of every queued hour, exchange hours included
 };
 struct ExchangeOps {
     virtual ~ExchangeOps() {}

@@ -70,7 +70,7 @@ EPI_HD uint64_t philox_draw(uint64_t seed, uint32_t agent, uint32_t hour, uint32
 }
 
 // rand 0.8 `Rng::gen_bool(p)`: Bernoulli::new(p) -> p == 1.0 always true, else p_int = (p * 2^64) as u64, sample u64 < p_int.
-inline uint64_t bernoulli_threshold(double p) {
+EPI_HD uint64_t bernoulli_threshold(double p) {
     if (p >= 1.0) return UINT64_MAX;  // "always" sentinel
     if (p <= 0.0) return 0;
     return (uint64_t)(p * 18446744073709551616.0);

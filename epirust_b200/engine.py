@@ -318,6 +318,14 @@ class Engine:
             self._check(self.L.epi_outgoing_travels(self.h, _ptr(out), n.value, C.byref(n)))
         return out
 
+    def debug_trace(self):
+        """EPI_TRACE=1: [(tag, nanoseconds, hour)] stamps left by the kernels since the last call"""
+        buf = np.zeros(1 << 16, np.uint64)
+        n = C.c_uint64(0)
+        self._check(self.L.epi_debug_trace(self.h, _ptr(buf), len(buf), C.byref(n)))
+        w = buf[: n.value].reshape(-1, 2)
+        return [(int(a >> np.uint64(56)), int(a & np.uint64((1 << 56) - 1)), int(h)) for a, h in w]
+
     def set_tiles(self, on):
         """tile kernels of the plain movement hours on / off (same results either way)"""
         self._check(self.L.epi_set_tiles(self.h, int(on)))

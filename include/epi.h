@@ -310,6 +310,10 @@ uint64_t epi_epoch_resets(const epi_engine* e);
  * creation), epi_tile_hours counts the hours that took them.  (No reference equivalent.) */
 int epi_set_tiles(epi_engine* e, int on);
 uint64_t epi_tile_hours(const epi_engine* e);
+/* Debugging: with EPI_TRACE=1 in the environment at creation the kernels leave nanosecond stamps (pairs: (tag << 56) | time, hour; tag 1 = a
+ * commit pass starts, 2 / 3 = the exchange's leave kernel starts / ends, 4 / 5 / 6 = its arrive kernel starts / has every peer's travellers / ends).
+ * Returns and clears them. */
+int epi_debug_trace(epi_engine* e, uint64_t* out, uint64_t max_words, uint64_t* n_words);
 
 /* ---- host driver: the engine-app equivalent ----------------------------------------------------------------- */
 /* Parse the reference's simulation-config JSON (common::config::Config::read, common/src/config/mod.rs:124-128). */

@@ -21,23 +21,25 @@ def plan(migration=True, commute=True, start=48, end=336):
                 start_migration_hour=start, end_migration_hour=end)
 
 
-def test_a_day_has_three_waits_and_rows_land_in_order():
+def test_a_day_has_one_wait_and_rows_land_in_order():
     calls = multi_schedule_trace(plan(), 49, 24)  # hours 49..72: day 3, inside the migration window
     assert [c for c in calls if c[0] != "exchange"] == [
-        ("hours", 49, 6), ("exchange_hour", 55), ("collect", list(range(49, 55))), ("finish", 55),      # 07:00 commuters leave
-        ("hours", 56, 9), ("exchange_hour", 65), ("collect", list(range(56, 65))), ("finish", 65),      # 17:00 commuters return
-        ("hours", 66, 6), ("exchange_hour", 72), ("collect", list(range(66, 72))), ("finish", 72),      # 00:00 migrators
+        ("hours", 49, 6), ("exchange_hour", 55),      # 07:00 commuters leave
+        ("hours", 56, 9), ("exchange_hour", 65),      # 17:00 commuters return
+        ("hours", 66, 6), ("exchange_hour", 72),      # 00:00 migrators
+        ("collect", list(range(49, 73))),             # the only wait of the day: midnight is a decision hour (lockdown.rs:55, hospital.rs:55,70)
     ]
     assert [c for c in calls if c[0] == "exchange"] == [("exchange", 55, _ffi.TRAVEL_COMMUTE), ("exchange", 65, _ffi.TRAVEL_COMMUTE), ("exchange", 72, _ffi.TRAVEL_MIGRATE)]
-    # the exchange is queued right behind its hour's kernels, before the host waits
+    # the exchange is queued right behind its hour's kernels, and the next hours right behind the exchange: the host does not wait
     assert calls.index(("exchange", 55, _ffi.TRAVEL_COMMUTE)) == calls.index(("exchange_hour", 55)) + 1
+    assert calls.index(("hours", 56, 9)) == calls.index(("exchange", 55, _ffi.TRAVEL_COMMUTE)) + 1
 
 
 def test_outside_the_migration_window_midnight_is_a_plain_decision_hour():
     calls = multi_schedule_trace(plan(), 18, 14)  # hours 18..31: midnight (24) is before start_migration_hour = 48
     assert [c for c in calls if c[0] != "exchange"] == [
         ("hours", 18, 7), ("collect", list(range(18, 25))),  # the host sees hour 24 before hour 25 runs (lockdown.rs:55)
-        ("hours", 25, 6), ("exchange_hour", 31), ("collect", list(range(25, 31))), ("finish", 31)]
+        ("hours", 25, 6), ("exchange_hour", 31), ("collect", list(range(25, 32)))]
 
 
 @pytest.mark.parametrize("vaccinate_at,unlock_at", [((30,), 0), ((), 54), ((54,), 60)])
@@ -52,16 +54,19 @@ def test_no_hour_runs_before_a_decision_that_precedes_it(vaccinate_at, unlock_at
         elif c[0] == "collect":
             seen |= set(c[1])
             rows += c[1]
-        elif c[0] == "finish":
-            seen.add(c[1])
-            rows.append(c[1])
     assert rows == list(range(25, 73))
 
 
 def test_decision_hour_right_before_an_exchange_is_collected_first():
     calls = multi_schedule_trace(plan(), 49, 8, vaccinate_hours=(54,))  # vaccination at 06:00, commuters leave at 07:00 (hour 55)
     assert [c for c in calls if c[0] != "exchange"] == [
-        ("hours", 49, 6), ("collect", list(range(49, 55))), ("exchange_hour", 55), ("collect", []), ("finish", 55), ("hours", 56, 1), ("collect", [56])]
+        ("hours", 49, 6), ("collect", list(range(49, 55))), ("exchange_hour", 55), ("hours", 56, 1), ("collect", [55, 56])]
+
+
+def test_a_decision_at_an_exchange_hour_waits_after_the_exchange():
+    calls = multi_schedule_trace(plan(), 49, 10, vaccinate_hours=(55,))  # vaccination at 07:00 = the hour the commuters leave
+    assert calls == [("hours", 49, 6), ("exchange_hour", 55), ("exchange", 55, _ffi.TRAVEL_COMMUTE), ("collect", list(range(49, 56))),
+                     ("hours", 56, 3), ("collect", [56, 57, 58])]
 
 
 def test_every_rank_issues_the_same_collectives_whatever_its_own_decision_hours():

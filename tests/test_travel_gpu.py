@@ -131,7 +131,7 @@ def test_segment_overflow_is_reported_and_leaves_the_region_intact():
 
 def test_crowded_housing_needs_more_than_three_placement_rounds():
     """select_starting_points (allocation_map.rs:339-347) in a housing strip that is ~97 % full at midnight: some arrival finds all
-    24 candidates of the first three rounds taken, so the host's settle loop (travel.cpp) must run further rounds."""
+    24 candidates of the first three rounds taken, so the placement kernel (k_travel_place) must loop beyond three rounds."""
     R = 2
     kw = dict(n_agents=1420, grid_size=60, hours=200, exposed=20, pt=0.0, working=0.2)
     plan = dict(n_regions=R, migration=np.array([[0, 15], [15, 0]], np.uint32), start_migration_hour=20, end_migration_hour=150)

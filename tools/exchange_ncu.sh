@@ -10,7 +10,7 @@ from bench import WORKLOADS, travel_plan_for
 kw = dict(WORKLOADS['10m']); n = kw['n_agents']; R = 2
 plan = travel_plan_for(R, n)
 engines = [Engine(make_config(hours=2000, **kw), seed=1 + r, device=0, region=r, plan=plan, extra_capacity=n // 25) for r in range(R)]
-m = MultiRegion(engines, plan, stride_records=2 * (n // 1000) + 4096)
+m = MultiRegion(engines)
 m.run(1, 73)
 PY
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"k_travel|k_occ" --csv --log-file gpurun_out/travel_kernels.csv python /tmp/x.py > gpurun_out/travel_ncu.log 2>&1
