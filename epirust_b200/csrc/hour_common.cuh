@@ -45,6 +45,13 @@ __device__ __forceinline__ uint32_t ld_plain(const uint32_t* p) {  // the tile k
 // ahead as well costs more issue slots than it saves).
 constexpr uint32_t PREFETCH_AHEAD = 148u * 6u * 256u;  // one wave of k_hour: 148 SMs x 48 warps
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// Programmatic dependent launch (the kernels of a simulated day are launched with programmaticStreamSerialization, kernels.cu):
+// pdl_wait() returns when the previous kernel of the stream has completed and its writes are visible; pdl_launch() lets the
+// next kernel's CTAs become resident as soon as every CTA of this one has got this far.  Each kernel calls wait then launch
+// before it touches anything a neighbour in the stream writes, so a kernel's CTAs overlap only the tail of its predecessor and
+// the chain hour -> commit -> hour stays ordered through the waits.  Both are no-ops in a launch without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void st_stream(uint32_t* p, uint32_t v) { asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
 __device__ __forceinline__ bool rect_contains(const Rect& r, int x, int y) { return r.sx <= x && r.ex >= x && r.sy <= y && r.ey >= y; }
