@@ -203,6 +203,10 @@ struct GlobalEnv {
     const DevPtrs& D;
     __device__ __forceinline__ void on_rule(int, const Rect&, int) {}
     __device__ __forceinline__ Window window(int cx, int cy) const { return load_window(D.grid, P, cx, cy); }
+    // an agent the hour does not concern: no proposal
+    __device__ __forceinline__ void commit_idle(uint32_t i) {
+        if (ALWAYS_WRITE_PROP) st_stream(D.prop + i, 0u);
+    }
     // the agent stands on (x, y), proposes (tx, ty); `dirty`: its grid byte changes; byte = its new grid byte
     __device__ __forceinline__ void commit(uint32_t i, uint32_t hour, int x, int y, int tx, int ty, bool dirty, uint32_t byte) {
         uint32_t prop = dirty ? PROP_DIRTY : 0u;
@@ -227,6 +231,16 @@ __device__ __forceinline__ void agent_hour(const Params& P, const DevPtrs& D, ui
     constexpr uint32_t h = HOD;
     // one round trip: the agent's state words (and the uniform clock word)
     const uint32_t s0 = Env::stream_loads ? ld_early_rw(D.st + i) : ld_plain(D.st + i);
+    if constexpr (KIND != KIND_MOVE) {
+        // ROUTINE_START_TIME only concerns the infected, ROUTINE_END_TIME the infected and the recovered (citizen/mod.rs:240-243,
+        // :397-413): everybody else is done after the state word -- cell and home are not even requested (these two passes
+        // stream 80 MB instead of 160 MB at 10 M agents while the infected are few)
+        const uint32_t st0 = s0 & ST_STATE_MASK;
+        if (!(st0 == ST_I || (KIND == KIND_END && st0 == ST_R))) {
+            if (st0 != ST_ABSENT) env.commit_idle(i);
+            return;
+        }
+    }
     const uint32_t c0 = Env::stream_loads ? ld_early_rw(D.cell + i) : ld_plain(D.cell + i);
     const uint32_t hm = Env::stream_loads ? ld_early(D.home + i) : ld_plain(D.home + i);
     const uint32_t wk = KIND == KIND_MOVE ? (Env::stream_loads ? ld_early(D.work + i) : ld_plain(D.work + i)) : 0u;
