@@ -44,14 +44,8 @@ __device__ __forceinline__ uint32_t ld_plain(const uint32_t* p) {  // the tile k
 // (+5 % agent-steps/s at 10 M agents; half a wave is as good, 2 and 4 waves are worse; prefetching the grid rows of the agent
 // ahead as well costs more issue slots than it saves).
 constexpr uint32_t PREFETCH_AHEAD = 148u * 6u * 256u;  // one wave of k_hour: 148 SMs x 48 warps
+constexpr uint32_t PREFETCH_MIN_AGENTS = 4u << 20;       // below this the per-agent arrays (32 B per agent) and the grids fit the 126 MB L2
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-// Programmatic dependent launch (the kernels of a simulated day are launched with programmaticStreamSerialization, kernels.cu):
-// pdl_wait() returns when the previous kernel of the stream has completed and its writes are visible; pdl_launch() lets the
-// next kernel's CTAs become resident as soon as every CTA of this one has got this far.  Each kernel calls wait then launch
-// before it touches anything a neighbour in the stream writes, so a kernel's CTAs overlap only the tail of its predecessor and
-// the chain hour -> commit -> hour stays ordered through the waits.  Both are no-ops in a launch without the attribute.
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void st_stream(uint32_t* p, uint32_t v) { asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
 __device__ __forceinline__ bool rect_contains(const Rect& r, int x, int y) { return r.sx <= x && r.ex >= x && r.sy <= y && r.ey >= y; }
@@ -203,10 +197,6 @@ struct GlobalEnv {
     const DevPtrs& D;
     __device__ __forceinline__ void on_rule(int, const Rect&, int) {}
     __device__ __forceinline__ Window window(int cx, int cy) const { return load_window(D.grid, P, cx, cy); }
-    // an agent the hour does not concern: no proposal
-    __device__ __forceinline__ void commit_idle(uint32_t i) {
-        if (ALWAYS_WRITE_PROP) st_stream(D.prop + i, 0u);
-    }
     // the agent stands on (x, y), proposes (tx, ty); `dirty`: its grid byte changes; byte = its new grid byte
     __device__ __forceinline__ void commit(uint32_t i, uint32_t hour, int x, int y, int tx, int ty, bool dirty, uint32_t byte) {
         uint32_t prop = dirty ? PROP_DIRTY : 0u;
@@ -231,16 +221,6 @@ __device__ __forceinline__ void agent_hour(const Params& P, const DevPtrs& D, ui
     constexpr uint32_t h = HOD;
     // one round trip: the agent's state words (and the uniform clock word)
     const uint32_t s0 = Env::stream_loads ? ld_early_rw(D.st + i) : ld_plain(D.st + i);
-    if constexpr (KIND != KIND_MOVE) {
-        // ROUTINE_START_TIME only concerns the infected, ROUTINE_END_TIME the infected and the recovered (citizen/mod.rs:240-243,
-        // :397-413): everybody else is done after the state word -- cell and home are not even requested (these two passes
-        // stream 80 MB instead of 160 MB at 10 M agents while the infected are few)
-        const uint32_t st0 = s0 & ST_STATE_MASK;
-        if (!(st0 == ST_I || (KIND == KIND_END && st0 == ST_R))) {
-            if (st0 != ST_ABSENT) env.commit_idle(i);
-            return;
-        }
-    }
     const uint32_t c0 = Env::stream_loads ? ld_early_rw(D.cell + i) : ld_plain(D.cell + i);
     const uint32_t hm = Env::stream_loads ? ld_early(D.home + i) : ld_plain(D.home + i);
     const uint32_t wk = KIND == KIND_MOVE ? (Env::stream_loads ? ld_early(D.work + i) : ld_plain(D.work + i)) : 0u;
@@ -373,9 +353,16 @@ __device__ __forceinline__ void agent_hour(const Params& P, const DevPtrs& D, ui
             // not possible: a relocated walker / a goto that found its point occupied stays at (x, y), which
             // is outside the window -> second load (hours 7, 8, 16, 17 mostly)
             Hood hd;
-            if (tx == bx + ddx && ty == by + ddy) hd = hood_at(win, ddx, ddy);
-            else hd = hood_centre(env.window(tx, ty));
-            uint32_t inf = infectious_mask(hd);
+            uint32_t inf = 0;
+            const bool in_window = tx == bx + ddx && ty == by + ddy;
+            // nobody infectious anywhere in the 5x5 window (the usual case outside the peak of the epidemic): no neighbourhood to
+            // assemble.  Six logic instructions against the ~25 of hood_at + infectious_mask.
+            const uint32_t any_inf = (win.l[0] | win.r[0] | win.l[1] | win.r[1] | win.l[2] | win.r[2] | win.l[3] | win.r[3] | win.l[4] | win.r[4]) & 0x02020202u;
+            if (!in_window || any_inf) {
+                if (in_window) hd = hood_at(win, ddx, ddy);
+                else hd = hood_centre(env.window(tx, ty));
+                inf = infectious_mask(hd);
+            }
             // neighbours are clipped to the NEW current_area: R is its rectangle unless a non-working agent's
             // area changed this hour (h = 8, 12), where R is still the old one
             if (inf) inf &= valid_mask(kind == kind0 ? R : rect_of(kind), P.grid_size, tx, ty);

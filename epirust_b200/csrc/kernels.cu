@@ -34,8 +34,6 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#include <cstdlib>
-
 #include "hour_common.cuh"
 #include "kernels.h"
 
@@ -72,14 +70,13 @@ template <int KIND, bool INJECT, uint32_t HOD = 0>
 __global__ void __launch_bounds__(EPI_HBS, KIND == KIND_MOVE ? EPI_MINB * (256 / EPI_HBS) : 4 * (256 / EPI_HBS)) k_hour(Params P, DevPtrs D, uint32_t hour_offset) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n) return;
-    if ((threadIdx.x & 7u) == 0 && i + PREFETCH_AHEAD < P.n) {  // one prefetch per 32-byte sector
+    // (a population whose arrays stay in the L2 anyway gains nothing from it: 1 M agents run 1 % faster without)
+    if (P.n >= PREFETCH_MIN_AGENTS && (threadIdx.x & 7u) == 0 && i + PREFETCH_AHEAD < P.n) {  // one prefetch per 32-byte sector
         prefetch_l2(D.st + i + PREFETCH_AHEAD);
         prefetch_l2(D.cell + i + PREFETCH_AHEAD);
         prefetch_l2(D.home + i + PREFETCH_AHEAD);
         if (KIND == KIND_MOVE) prefetch_l2(D.work + i + PREFETCH_AHEAD);
     }
-    pdl_wait();  // the prefetches above only warm the L2 (coherent); everything below reads what k_commit / k_sleep wrote
-    pdl_launch();
     GlobalEnv<true> env{P, D};
     agent_hour<KIND, INJECT, HOD>(P, D, i, D.clock->hour_base + hour_offset, env);
 }
@@ -106,8 +103,6 @@ __device__ __forceinline__ void st_stream4(uint32_t* p, uint32_t a, uint32_t b, 
 template <bool LAZY>
 __global__ void __launch_bounds__(256) k_commit(Params P, DevPtrs D, uint32_t hour_offset, uint32_t zero_props) {
     const uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4u;
-    pdl_wait();
-    pdl_launch();
     const uint32_t hour = D.clock->hour_base + hour_offset;
     if (blockIdx.x == 0 && threadIdx.x == 0) trace_stamp(D.trace, 1, hour);
     if (blockIdx.x == 0 && threadIdx.x < 32) {
@@ -203,8 +198,6 @@ __global__ void __launch_bounds__(256) k_sleep(Params P, DevPtrs D, uint32_t hou
     if (threadIdx.x < 6) s_cnt[threadIdx.x] = 0;
     __syncthreads();
     const uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4u;
-    pdl_wait();
-    pdl_launch();
     const uint32_t hour = D.clock->hour_base + hour_offset;
     uint32_t st[4] = {ST_ABSENT, ST_ABSENT, ST_ABSENT, ST_ABSENT};
     const bool full = i0 + 3u < P.n;
@@ -316,26 +309,6 @@ __global__ void __launch_bounds__(256) k_import_state(Params P, DevPtrs D, const
 
 // ---- launchers ---------------------------------------------------------------------------------------------------
 static inline unsigned blocks_for(uint32_t n) { return (n + 255u) / 256u; }
-// The kernels of the hour loop (k_hour, k_commit, k_sleep) are launched with programmatic stream serialization: the next
-// kernel's CTAs are scheduled while the last wave of this one drains (see pdl_wait / pdl_launch); captured into the day graph the
-// attribute becomes a programmatic dependency edge.  Off unless EPI_PDL=1 until measured.
-static bool pdl_enabled() {
-    static const bool on = [] { const char* v = std::getenv("EPI_PDL"); return v && v[0] == '1'; }();
-    return on;
-}
-template <class... KArgs, class... Args>
-static void launch_chain(void (*kernel)(KArgs...), unsigned blocks, unsigned threads, cudaStream_t s, Args&&... args) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(blocks);
-    cfg.blockDim = dim3(threads);
-    cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = pdl_enabled() ? 1 : 0;
-    cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
-}
 void launch_import_state(const Params& P, const DevPtrs& D, const int32_t* cx, const int32_t* cy, uint32_t n_houses, uint32_t n_offices, uint32_t* bad, cudaStream_t s) {
     k_import_state<<<blocks_for(P.n), 256, 0, s>>>(P, D, cx, cy, n_houses, n_offices, bad);
 }
@@ -352,14 +325,14 @@ template <bool INJECT>
 static void launch_hour_t(const Params& P, const DevPtrs& D, uint32_t hour_of_day, uint32_t hour_offset, cudaStream_t s) {
     const unsigned b = (P.n + EPI_HBS - 1u) / EPI_HBS;
     switch (hour_of_day) {
-        case 0: launch_chain(k_hour<KIND_START, INJECT>, b, EPI_HBS, s, P, D, hour_offset); break;
-        case 23: launch_chain(k_hour<KIND_END, INJECT>, b, EPI_HBS, s, P, D, hour_offset); break;
-        case 7: launch_chain(k_hour<KIND_MOVE, INJECT, 7>, b, EPI_HBS, s, P, D, hour_offset); break;
-        case 8: launch_chain(k_hour<KIND_MOVE, INJECT, 8>, b, EPI_HBS, s, P, D, hour_offset); break;
-        case 12: launch_chain(k_hour<KIND_MOVE, INJECT, 12>, b, EPI_HBS, s, P, D, hour_offset); break;
-        case 16: launch_chain(k_hour<KIND_MOVE, INJECT, 16>, b, EPI_HBS, s, P, D, hour_offset); break;
-        case 17: launch_chain(k_hour<KIND_MOVE, INJECT, 17>, b, EPI_HBS, s, P, D, hour_offset); break;
-        default: launch_chain(k_hour<KIND_MOVE, INJECT, 9>, b, EPI_HBS, s, P, D, hour_offset); break;  // 9..11, 13..15, 18..22 (1..6 are k_sleep's)
+        case 0: k_hour<KIND_START, INJECT><<<b, EPI_HBS, 0, s>>>(P, D, hour_offset); break;
+        case 23: k_hour<KIND_END, INJECT><<<b, EPI_HBS, 0, s>>>(P, D, hour_offset); break;
+        case 7: k_hour<KIND_MOVE, INJECT, 7><<<b, EPI_HBS, 0, s>>>(P, D, hour_offset); break;
+        case 8: k_hour<KIND_MOVE, INJECT, 8><<<b, EPI_HBS, 0, s>>>(P, D, hour_offset); break;
+        case 12: k_hour<KIND_MOVE, INJECT, 12><<<b, EPI_HBS, 0, s>>>(P, D, hour_offset); break;
+        case 16: k_hour<KIND_MOVE, INJECT, 16><<<b, EPI_HBS, 0, s>>>(P, D, hour_offset); break;
+        case 17: k_hour<KIND_MOVE, INJECT, 17><<<b, EPI_HBS, 0, s>>>(P, D, hour_offset); break;
+        default: k_hour<KIND_MOVE, INJECT, 9><<<b, EPI_HBS, 0, s>>>(P, D, hour_offset); break;  // 9..11, 13..15, 18..22 (1..6 are k_sleep's)
     }
 }
 void launch_hour(const Params& P, const DevPtrs& D, uint32_t hour_of_day, uint32_t hour_offset, bool inject, cudaStream_t s) {
@@ -369,10 +342,10 @@ void launch_hour(const Params& P, const DevPtrs& D, uint32_t hour_of_day, uint32
 void launch_recount(const Params& P, const DevPtrs& D, cudaStream_t s) { k_recount<<<blocks_for(P.n), 256, 0, s>>>(P, D.st, D.tot); }
 void launch_set_clock(Clock* clock, const Clock& value, cudaStream_t s) { k_set_clock<<<1, 1, 0, s>>>(clock, value); }
 void launch_commit(const Params& P, const DevPtrs& D, uint32_t hour_offset, bool lazy, bool zero_props, cudaStream_t s) {
-    if (lazy) launch_chain(k_commit<true>, blocks_for((P.n + 3u) / 4u), 256u, s, P, D, hour_offset, 1u);
-    else launch_chain(k_commit<false>, blocks_for((P.n + 3u) / 4u), 256u, s, P, D, hour_offset, zero_props ? 1u : 0u);
+    if (lazy) k_commit<true><<<blocks_for((P.n + 3u) / 4u), 256, 0, s>>>(P, D, hour_offset, 1u);
+    else k_commit<false><<<blocks_for((P.n + 3u) / 4u), 256, 0, s>>>(P, D, hour_offset, zero_props ? 1u : 0u);
 }
-void launch_sleep(const Params& P, const DevPtrs& D, uint32_t hour_offset, cudaStream_t s) { launch_chain(k_sleep, blocks_for((P.n + 3u) / 4u), 256u, s, P, D, hour_offset); }
+void launch_sleep(const Params& P, const DevPtrs& D, uint32_t hour_offset, cudaStream_t s) { k_sleep<<<blocks_for((P.n + 3u) / 4u), 256, 0, s>>>(P, D, hour_offset); }
 void launch_lock(const Params& P, const DevPtrs& D, cudaStream_t s) { k_lock<<<blocks_for(P.n), 256, 0, s>>>(P, D.st); }
 void launch_unlock(const Params& P, const DevPtrs& D, cudaStream_t s) { k_unlock<<<blocks_for(P.n), 256, 0, s>>>(P, D.st); }
 void launch_vaccinate(const Params& P, const DevPtrs& D, uint64_t thr, uint32_t hour, cudaStream_t s) { k_vaccinate<<<blocks_for(P.n), 256, 0, s>>>(P, D.st, thr, hour); }

@@ -13,5 +13,5 @@ for spec in sys.argv[1:]:
     o = os.path.join(ROOT, "exp", f"kernels_{name}.o")
     subprocess.check_call([B._nvcc()] + B.NVCC_FLAGS + ["-I", os.path.join(ROOT, "include")] + defs.split() + ["-Xptxas", "-v", "-c", os.path.join(B.CSRC, "kernels.cu"), "-o", o],
                           stderr=open(os.path.join(ROOT, "exp", f"ptxas_{name}.log"), "w"))
-    subprocess.check_call([B._nvcc(), "-shared", "-ccbin", "/usr/bin/g++", "-Xcompiler", "-fopenmp", "-o", os.path.join(ROOT, "exp", f"lib_{name}.so"), o] + objs)
+    subprocess.check_call([B._nvcc(), "-shared", "-ccbin", "/usr/bin/g++", "-Xcompiler", "-fopenmp", "-o", os.path.join(ROOT, "exp", f"lib_{name}.so"), o] + objs + ["-lnccl"])
     print("built", name, defs)
