@@ -187,6 +187,9 @@ struct Draws {
     }
 };
 
+// hour_base and epoch_base of the device-resident clock in one 64-bit load
+__device__ __forceinline__ uint2 load_clock(const Clock* c) { return *reinterpret_cast<const uint2*>(c); }
+
 // Where an agent-hour reads its grid windows and what becomes of its proposal.  GlobalEnv: the grid in global memory, the
 // proposal goes to prop[] + an atomicMax on claim[] for k_commit (kernels.cu).  tiles.cu has the shared-memory environment.
 enum : int { RC_HOME = 0, RC_OFFICE = 1, RC_ZONE = 2 };  // what kind of rectangle an agent's movement is confined to this hour
@@ -195,6 +198,7 @@ struct GlobalEnv {
     static constexpr bool stream_loads = STREAM;  // the per-agent words are read once per kernel: evict-first
     const Params& P;
     const DevPtrs& D;
+    uint32_t epoch_base;  // Clock::epoch_base, read together with hour_base by the caller (load_clock): one load instead of two
     __device__ __forceinline__ void on_rule(int, const Rect&, int) {}
     __device__ __forceinline__ Window window(int cx, int cy) const { return load_window(D.grid, P, cx, cy); }
     // the agent stands on (x, y), proposes (tx, ty); `dirty`: its grid byte changes; byte = its new grid byte
@@ -202,7 +206,7 @@ struct GlobalEnv {
         uint32_t prop = dirty ? PROP_DIRTY : 0u;
         if (tx != x || ty != y) {
             prop |= PROP_MOVE | ((uint32_t)ty << CELL_BITS) | (uint32_t)tx;
-            const uint32_t stamp = hour - D.clock->epoch_base + 1u;
+            const uint32_t stamp = hour - epoch_base + 1u;
             const uint32_t id_mask = (1u << P.id_bits) - 1u;
             atomicMax(&D.claim[P.cell_offset(tx, ty)], (stamp << P.id_bits) | (id_mask - i));
         }
@@ -232,6 +236,7 @@ __device__ __forceinline__ void agent_hour(const Params& P, const DevPtrs& D, ui
     const Draws<INJECT> dr{P, i, hour, INJECT ? D.draws + (size_t)i * 16 : nullptr};
     const uint32_t ws = (s0 >> ST_WS_SHIFT) & 3u;
     uint32_t state = s0 & ST_STATE_MASK, sev = (s0 >> ST_SEV_SHIFT) & 3u, day = s0 >> ST_DAY_SHIFT;
+    bool transition = KIND != KIND_MOVE;  // state / sev / day may differ from s0: the state word is re-packed at the end
     const Rect home = origin_rect(hm, 1);
 
     if (KIND == KIND_START) {
@@ -278,12 +283,15 @@ __device__ __forceinline__ void agent_hour(const Params& P, const DevPtrs& D, ui
         // at_hour of Exposed / Pre: requested now, consumed after the window arrives
         uint32_t t0v = 0;
         if (state == ST_E || pre) t0v = ld_early_rw(D.t0 + i);
-        const Rect workr = ws == WS_NA ? home : origin_rect(wk, 9);
+        // Citizen.work_location of a non-working agent is its home (citizen_factory.rs:62-64).  The packed origin is chosen first
+        // and unpacked once (the ALU pipe is this kernel's limit: every select and shift counts).
         auto rect_of = [&](uint32_t kind) -> Rect {
-            Rect r = kind == AK_WORK ? workr : home;
+            const bool office = kind == AK_WORK && ws != WS_NA;
+            Rect r = origin_rect(office ? wk : hm, office ? 9 : 1);
             if (kind >= AK_TRANSPORT) r = P.zone[kind - AK_TRANSPORT];
             return r;
         };
+        auto work_rect = [&]() -> Rect { return rect_of(AK_WORK); };
         // the hour's rule -> (mode, rectangle R, new current_area kind).  goto_area for a non-working agent is
         // move_agent_from in the (old) current_area (citizen/mod.rs:386-394), i.e. MODE_WALK.
         auto class_of = [&](uint32_t kind) -> int { return kind >= AK_TRANSPORT ? RC_ZONE : (kind == AK_WORK && ws != WS_NA) ? RC_OFFICE : RC_HOME; };
@@ -298,10 +306,10 @@ __device__ __forceinline__ void agent_hour(const Params& P, const DevPtrs& D, ui
         } else if (ws != WS_STAFF) {  // Normal | Essential
             if (h == 7 || h == 17) {
                 if (s0 & ST_PT) { mode = MODE_GOTO; R = P.transport(); kind = AK_TRANSPORT; rcls = RC_ZONE; }
-            } else if (h == 8) { mode = MODE_GOTO; R = workr; kind = AK_WORK; rcls = RC_OFFICE; }
+            } else if (h == 8) { mode = MODE_GOTO; R = work_rect(); kind = AK_WORK; rcls = RC_OFFICE; }
             else if (h == 16) {
                 mode = MODE_GOTO; R = home; kind = AK_HOME; rcls = RC_HOME;
-                override_movement = symptomatic && rect_contains(workr, x, y);  // citizen/mod.rs:373-381
+                override_movement = symptomatic && rect_contains(work_rect(), x, y);  // citizen/mod.rs:373-381
             }
         } else {  // HospitalStaff { work_start_at } (0.14 % of agents)
             const uint32_t wsa = D.wsa[i];
@@ -372,6 +380,7 @@ __device__ __forceinline__ void agent_hour(const Params& P, const DevPtrs& D, ui
                 const uint32_t b = ((j < 4 ? hd.lo : hd.hi) >> (8 * (j & 3))) & CELL_OCC_MASK;
                 if (bernoulli(dr.expose(j), P.thr_rate[b - 1u])) {
                     state = ST_E;
+                    transition = true;
                     D.t0[i] = hour;
                     break;
                 }
@@ -383,17 +392,19 @@ __device__ __forceinline__ void agent_hour(const Params& P, const DevPtrs& D, ui
                 const int f = (int)__umulhi(factor, 3u) - 1;
                 if (hour - t0v >= (uint32_t)((int)P.exposed_duration + f)) {
                     const bool symptoms = bernoulli(a, P.thr_symptomatic);
+                    transition = true;
                     state = ST_I; day = 0;
                     sev = symptoms ? SEV_PRE : SEV_ASYM;
                     if (symptoms) D.t0[i] = hour;
                 }
             } else if (pre) {  // on_infected, :41-50
-                if (hour - t0v >= P.pre_symptomatic_duration) sev = bernoulli(a, P.thr_severe) ? SEV_SEVERE : SEV_MILD;
+                if (hour - t0v >= P.pre_symptomatic_duration) { sev = bernoulli(a, P.thr_severe) ? SEV_SEVERE : SEV_MILD; transition = true; }
             }
         }
     }
-    // re-pack
-    s = (s & ~(ST_STATE_MASK | (3u << ST_SEV_SHIFT) | (ST_DAY_MAX << ST_DAY_SHIFT))) | state | (sev << ST_SEV_SHIFT) | (day << ST_DAY_SHIFT);
+    // re-pack (a movement hour changes state / severity / day only through one of the transitions above)
+    if (transition)
+        s = (s & ~(ST_STATE_MASK | (3u << ST_SEV_SHIFT) | (ST_DAY_MAX << ST_DAY_SHIFT))) | state | (sev << ST_SEV_SHIFT) | (day << ST_DAY_SHIFT);
     bool dirty = false;
     if (s != s0) {
         st_stream(D.st + i, s);

@@ -70,15 +70,19 @@ template <int KIND, bool INJECT, uint32_t HOD = 0>
 __global__ void __launch_bounds__(EPI_HBS, KIND == KIND_MOVE ? EPI_MINB * (256 / EPI_HBS) : 4 * (256 / EPI_HBS)) k_hour(Params P, DevPtrs D, uint32_t hour_offset) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n) return;
-    // (a population whose arrays stay in the L2 anyway gains nothing from it: 1 M agents run 1 % faster without)
-    if (P.n >= PREFETCH_MIN_AGENTS && (threadIdx.x & 7u) == 0 && i + PREFETCH_AHEAD < P.n) {  // one prefetch per 32-byte sector
-        prefetch_l2(D.st + i + PREFETCH_AHEAD);
-        prefetch_l2(D.cell + i + PREFETCH_AHEAD);
-        prefetch_l2(D.home + i + PREFETCH_AHEAD);
-        if (KIND == KIND_MOVE) prefetch_l2(D.work + i + PREFETCH_AHEAD);
-    }
-    GlobalEnv<true> env{P, D};
-    agent_hour<KIND, INJECT, HOD>(P, D, i, D.clock->hour_base + hour_offset, env);
+    // L2 prefetch of the words the thread one wave ahead loads first, one per 32-byte sector (a population whose arrays stay in
+    // the L2 anyway gains nothing from it: 1 M agents run 1 % faster without).  Predicated, not branched, and with the distance
+    // as an immediate offset, so the addresses are the ones agent_hour's own loads use.
+    const uint32_t pf = P.n >= PREFETCH_MIN_AGENTS && (threadIdx.x & 7u) == 0 && i + PREFETCH_AHEAD < P.n;
+    if (KIND == KIND_MOVE)
+        asm volatile("{\n .reg .pred p;\n setp.ne.u32 p, %4, 0;\n @p prefetch.global.L2 [%0 + %5];\n @p prefetch.global.L2 [%1 + %5];\n @p prefetch.global.L2 [%2 + %5];\n @p prefetch.global.L2 [%3 + %5];\n}"
+                     ::"l"(D.st + i), "l"(D.cell + i), "l"(D.home + i), "l"(D.work + i), "r"(pf), "n"(PREFETCH_AHEAD * 4u));
+    else
+        asm volatile("{\n .reg .pred p;\n setp.ne.u32 p, %3, 0;\n @p prefetch.global.L2 [%0 + %4];\n @p prefetch.global.L2 [%1 + %4];\n @p prefetch.global.L2 [%2 + %4];\n}"
+                     ::"l"(D.st + i), "l"(D.cell + i), "l"(D.home + i), "r"(pf), "n"(PREFETCH_AHEAD * 4u));
+    const uint2 clk = load_clock(D.clock);  // hour_base, epoch_base
+    GlobalEnv<true> env{P, D, clk.y};
+    agent_hour<KIND, INJECT, HOD>(P, D, i, clk.x + hour_offset, env);
 }
 
 

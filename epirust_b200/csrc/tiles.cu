@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(256) k_count_housing(Params P, const uint32_t*
 struct MarkEnv : GlobalEnv<false> {
     const TileGeom& G;
     uint32_t* dirty;
-    __device__ __forceinline__ MarkEnv(const Params& P_, const DevPtrs& D_, const TileGeom& G_, uint32_t* dirty_) : GlobalEnv<false>{P_, D_}, G(G_), dirty(dirty_) {}
+    __device__ __forceinline__ MarkEnv(const Params& P_, const DevPtrs& D_, const TileGeom& G_, uint32_t* dirty_) : GlobalEnv<false>{P_, D_, D_.clock->epoch_base}, G(G_), dirty(dirty_) {}
     __device__ __forceinline__ void on_rule(int rcls, const Rect& R, int mode) {
         if (rcls == G.cls && mode != MODE_STAY) dirty[tile_of_origin(G, R.sx, R.sy)] = 1u;
     }
@@ -177,7 +177,7 @@ struct TileEnv {
     }
     __device__ __forceinline__ void commit(uint32_t i, uint32_t hour, int x_, int y_, int tx_, int ty_, bool dirty_, uint32_t byte_) {
         if (!local) {
-            GlobalEnv<false, false> g{P, D};
+            GlobalEnv<false, false> g{P, D, D.clock->epoch_base};
             g.commit(i, hour, x_, y_, tx_, ty_, dirty_, byte_);
             return;
         }
@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(EPI_TILE_THREADS, EPI_TILE_MINB) k_hour_tile(P
     }
     // the riders (and the local members of a tile that is not settled on chip this hour): global path
     {
-        GlobalEnv<false, false> genv{P, D};
+        GlobalEnv<false, false> genv{P, D, D.clock->epoch_base};
         const uint32_t g0 = use ? a1 : a0;
         uint32_t i_cur = g0 + lane < a2 ? TP.perm[g0 + lane] : 0u;
         uint32_t i_nxt = g0 + 32u + lane < a2 ? TP.perm[g0 + 32u + lane] : 0u;
