@@ -69,15 +69,16 @@ struct Window {
     uint32_t l[5], r[5];
 };
 __device__ __forceinline__ Window load_window(const uint8_t* __restrict__ grid, const Params& P, int cx, int cy) {
-    const size_t first = P.cell_offset(cx - 2, cy - 2);  // the window's top-left cell; GRID_XOFF and pitch are multiples of 4
-    const uint32_t sh = (uint32_t)(first & 3u) * 8u;
-    const uint32_t* p = reinterpret_cast<const uint32_t*>(grid + (first & ~(size_t)3));
-    const uint32_t stride = P.pitch >> 2;
+    const uint32_t first = P.cell_index(cx - 2, cy - 2);  // the window's top-left cell; GRID_XOFF and pitch are multiples of 4
+    const uint32_t sh = (first & 3u) * 8u;
+    const uint32_t* g32 = reinterpret_cast<const uint32_t*>(grid);
+    const uint32_t w0 = first >> 2, stride = P.pitch >> 2;  // 32-bit word indices: one widening multiply-add per row address
     uint32_t a[5], b[5];
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
-        a[k] = __ldg(p + (size_t)k * stride);
-        b[k] = __ldg(p + (size_t)k * stride + 1);
+        const uint32_t* p = g32 + (w0 + (uint32_t)k * stride);
+        a[k] = __ldg(p);
+        b[k] = __ldg(p + 1);
     }
     Window win;
 #pragma unroll
@@ -204,11 +205,12 @@ struct GlobalEnv {
     // the agent stands on (x, y), proposes (tx, ty); `dirty`: its grid byte changes; byte = its new grid byte
     __device__ __forceinline__ void commit(uint32_t i, uint32_t hour, int x, int y, int tx, int ty, bool dirty, uint32_t byte) {
         uint32_t prop = dirty ? PROP_DIRTY : 0u;
-        if (tx != x || ty != y) {
-            prop |= PROP_MOVE | ((uint32_t)ty << CELL_BITS) | (uint32_t)tx;
+        const uint32_t target = ((uint32_t)ty << CELL_BITS) | (uint32_t)tx;
+        if (target != (((uint32_t)y << CELL_BITS) | (uint32_t)x)) {
+            prop |= PROP_MOVE | target;
             const uint32_t stamp = hour - epoch_base + 1u;
             const uint32_t id_mask = (1u << P.id_bits) - 1u;
-            atomicMax(&D.claim[P.cell_offset(tx, ty)], (stamp << P.id_bits) | (id_mask - i));
+            atomicMax(&D.claim[P.cell_index(tx, ty)], (stamp << P.id_bits) | (id_mask - i));
         }
         if (prop) prop |= (byte - 1u) << PROP_BYTE_SHIFT;
         if (ALWAYS_WRITE_PROP || prop) st_stream(D.prop + i, prop);
@@ -346,14 +348,16 @@ __device__ __forceinline__ void agent_hour(const Params& P, const DevPtrs& D, ui
         uint64_t a = 0;
         if (mode == MODE_WALK || (dynamics && (state == ST_E || pre))) dr.common(pick, factor, a);
         int ddx = 0, ddy = 0;  // proposed cell relative to the window centre (bx, by)
+        bool in_window = !need_point;  // the cell the agent ends up proposing / standing on is (bx + ddx, by + ddy), inside the loaded window
         if (mode == MODE_GOTO) {
-            if (((win.r[2] >> 8) & CELL_OCC_MASK) == 0) { tx = bx; ty = by; }  // target.get_random_point vacant -> go (citizen/mod.rs:387-392)
+            if (((win.r[2] >> 8) & CELL_OCC_MASK) == 0) { tx = bx; ty = by; in_window = true; }  // target.get_random_point vacant -> go (citizen/mod.rs:387-392)
         } else if (mode == MODE_WALK) {  // Citizen::move_agent_from (citizen/mod.rs:415-432)
             const uint32_t cand = vacant_mask(hood_centre(win)) & valid_mask_inside(R, P.grid_size, bx, by);
             if (cand) {  // candidates.choose(rng): the k-th candidate in iterator order, k uniform
                 const int j = select_bit(cand, __umulhi(pick, (uint32_t)__popc(cand)));
                 ddx = hood_dx(j); ddy = hood_dy(j);
                 tx = bx + ddx; ty = by + ddy;
+                in_window = true;
             }
         }
         if (scan) {  // on_susceptible at the proposed cell (disease_state_machine.rs:53-70, default_disease_handler.rs:64-86)
@@ -362,7 +366,6 @@ __device__ __forceinline__ void agent_hour(const Params& P, const DevPtrs& D, ui
             // is outside the window -> second load (hours 7, 8, 16, 17 mostly)
             Hood hd;
             uint32_t inf = 0;
-            const bool in_window = tx == bx + ddx && ty == by + ddy;
             // nobody infectious anywhere in the 5x5 window (the usual case outside the peak of the epidemic): no neighbourhood to
             // assemble.  Six logic instructions against the ~25 of hood_at + infectious_mask.
             const uint32_t any_inf = (win.l[0] | win.r[0] | win.l[1] | win.r[1] | win.l[2] | win.r[2] | win.l[3] | win.r[3] | win.l[4] | win.r[4]) & 0x02020202u;

@@ -95,7 +95,9 @@ struct Params {
     uint32_t rk[10][2];         // Philox round keys of `seed` (key schedule hoisted out of the kernels)
     int region;
     // byte offset of cell (x, y) in grid[], and its index in claim[]
-    __host__ __device__ size_t cell_offset(int x, int y) const { return (size_t)(y + (int)GRID_YOFF) * pitch + (size_t)(x + (int)GRID_XOFF); }
+    // (32-bit arithmetic: rows x pitch <= 16390 x 16400 < 2^32, and x + GRID_XOFF >= 0 for every cell a window can touch)
+    __host__ __device__ uint32_t cell_index(int x, int y) const { return (uint32_t)(y + (int)GRID_YOFF) * pitch + (uint32_t)(x + (int)GRID_XOFF); }
+    __host__ __device__ size_t cell_offset(int x, int y) const { return cell_index(x, y); }
     __host__ __device__ size_t cell_offset(uint32_t packed) const { return cell_offset((int)(packed & 0x3FFFu), (int)(packed >> 14)); }
     __host__ __device__ size_t grid_bytes() const { return (size_t)pitch * (rows + 2u * GRID_YOFF) + 2u * GRID_XOFF; }
     __host__ __device__ const Rect& transport() const { return zone[0]; }
