@@ -6,7 +6,7 @@
 //                     default_disease_handler.rs:31-103, counts.rs:126-140).  KIND: the hour-of-day class
 //                     (ROUTINE_START_TIME, ROUTINE_END_TIME, else perform_movements); HOD: the movement hour the kernel is
 //                     compiled for (7, 8, 12, 16, 17 or "any other") -- both uniform per launch.
-//   k_commit          four agents per thread: lowest-id claimant moves, loser stays; grid bytes updated in place
+//   k_commit_lanes    two agents per thread, 32 slots apart: lowest-id claimant moves, loser stays; grid bytes updated in place
 //                     (allocation_map.rs:93-102,131-134)
 //   k_sleep           hours 1..6, four agents per thread: current_area := home (citizen/mod.rs:244-248) + Counts recount
 //   k_lock / k_unlock / k_vaccinate   intervention sweeps (allocation_map.rs:349-387)
@@ -86,9 +86,11 @@ __global__ void __launch_bounds__(EPI_HBS, KIND == KIND_MOVE ? EPI_MINB * (256 /
 }
 
 
-// k_commit: four consecutive agents per thread.  The proposal and cell words arrive as two 128-bit loads, the (up to) four
-// claim words are requested together before anything is stored, so a warp has 4x the memory requests in flight of a
-// one-agent-per-thread version (the kernel is latency-bound: ~25 instructions per agent, two dependent round trips).
+// k_commit<LAZY = true>: the commit pass of a tile hour (tiles.cu), four consecutive agents per thread.  The proposal and cell words
+// arrive as two 128-bit loads, the (up to) four claim words are requested together before anything is stored.
+#ifndef EPI_COMMIT_APT
+#define EPI_COMMIT_APT 2u  // agents per thread of k_commit_lanes (ms per simulated day at 10 M / 1 M agents: 1: 4.72 / 0.522, 2: 4.54 / 0.511, 4: 4.56 / 0.528, 8: 4.59 / 0.547)
+#endif
 #ifndef EPI_CPF
 #define EPI_CPF 0u  // L2 prefetch distance in agents (0: none -- with four agents per thread it no longer pays: 97 us vs 99-101 us)
 #endif
@@ -192,6 +194,78 @@ __global__ void __launch_bounds__(256) k_commit(Params P, DevPtrs D, uint32_t ho
             for (uint32_t j = 0; j < 4; ++j)
                 if (i0 + j < P.n) D.prop[i0 + j] = 0u;
         }
+    }
+}
+
+// k_commit_lanes: the commit pass of the id-order hours.  The EPI_COMMIT_APT agents of a thread are 32 slots apart (agent = warp base
+// + 32 j + lane), so every load / store instruction of a warp covers 32 CONSECUTIVE agents: housemates sit in adjacent lanes and the
+// claim words and grid bytes one instruction touches share 128-byte lines (the L1 processes one line per cycle, which is this
+// kernel's limit), while a thread still has several claim loads in flight.  Against four consecutive agents per thread (k_commit
+// below, 128-bit loads): 96 -> 88 us per launch at 10 M agents, 17.4 -> 14.2 us at 1 M.
+__device__ __forceinline__ uint32_t ld_stream1(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.global.cs.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__global__ void __launch_bounds__(256) k_commit_lanes(Params P, DevPtrs D, uint32_t hour_offset, uint32_t zero_props) {
+    const uint32_t gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t wbase = (gt >> 5) * (32u * EPI_COMMIT_APT), base = wbase + (gt & 31u);
+    const uint32_t hour = D.clock->hour_base + hour_offset;
+    if (gt == 0) trace_stamp(D.trace, 1, hour);
+    if (blockIdx.x == 0 && threadIdx.x < 32) {
+        // the hour's Counts row = sum of the running totals' copies (all k_hour blocks of this hour have finished)
+#pragma unroll
+        for (uint32_t c = 0; c < 6; ++c) {
+            uint32_t v = threadIdx.x < TOT_COPIES ? D.tot[threadIdx.x * 8u + c] : 0u;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+            if (threadIdx.x == 0) D.counts[(size_t)(hour - D.clock->ring_base) * 8 + c] = v;
+        }
+    }
+    if (wbase >= P.n) return;
+    uint32_t prop[EPI_COMMIT_APT], c0[EPI_COMMIT_APT];
+#pragma unroll
+    for (uint32_t j = 0; j < EPI_COMMIT_APT; ++j) {
+        const uint32_t idx = base + 32u * j;
+        const bool in = idx < P.n;
+        prop[j] = in ? ld_stream1(D.prop + idx) : 0u;
+        c0[j] = in ? ld_stream1(D.cell + idx) : 0u;
+    }
+    uint32_t any = 0;
+#pragma unroll
+    for (uint32_t j = 0; j < EPI_COMMIT_APT; ++j) any |= prop[j];
+    if (any == 0) return;
+    if (zero_props) {  // the next hour is a tile hour: leave prop[] all zero
+#pragma unroll
+        for (uint32_t j = 0; j < EPI_COMMIT_APT; ++j)
+            if (prop[j]) st_stream(D.prop + base + 32u * j, 0u);
+    }
+    const uint32_t stamp = hour - D.clock->epoch_base + 1u;
+    const uint32_t id_mask = (1u << P.id_bits) - 1u;
+    uint32_t cl[EPI_COMMIT_APT];  // every claim word first: one round trip for the four agents
+#pragma unroll
+    for (uint32_t j = 0; j < EPI_COMMIT_APT; ++j) {
+        cl[j] = 0;
+        if (prop[j] & PROP_MOVE) cl[j] = __ldcg(D.claim + P.cell_index(prop[j] & PROP_CELL_MASK & CELL_XMASK, (prop[j] & PROP_CELL_MASK) >> CELL_BITS));
+    }
+#pragma unroll
+    for (uint32_t j = 0; j < EPI_COMMIT_APT; ++j) {
+        if (prop[j] == 0) continue;
+        const uint32_t idx = base + 32u * j;
+        const uint32_t byte = (prop[j] >> PROP_BYTE_SHIFT) + 1u;
+        const uint32_t at = P.cell_index(c0[j] & CELL_XMASK, c0[j] >> CELL_BITS);
+        if (prop[j] & PROP_MOVE) {
+            const uint32_t tc = prop[j] & PROP_CELL_MASK;
+            // lowest id among the claimants: upcoming.entry(new).or_insert (allocation_map.rs:93-98)
+            if (cl[j] == ((stamp << P.id_bits) | (id_mask - idx))) {
+                D.grid[at] = 0;
+                D.grid[P.cell_index(tc & CELL_XMASK, tc >> CELL_BITS)] = (uint8_t)byte;
+                st_stream(D.cell + idx, tc);
+                continue;
+            }
+            // lost: stays at old_cell (allocation_map.rs:99-102); still refresh the byte if it changed
+        }
+        if (prop[j] & PROP_DIRTY) D.grid[at] = (uint8_t)byte;
     }
 }
 
@@ -347,7 +421,7 @@ void launch_recount(const Params& P, const DevPtrs& D, cudaStream_t s) { k_recou
 void launch_set_clock(Clock* clock, const Clock& value, cudaStream_t s) { k_set_clock<<<1, 1, 0, s>>>(clock, value); }
 void launch_commit(const Params& P, const DevPtrs& D, uint32_t hour_offset, bool lazy, bool zero_props, cudaStream_t s) {
     if (lazy) k_commit<true><<<blocks_for((P.n + 3u) / 4u), 256, 0, s>>>(P, D, hour_offset, 1u);
-    else k_commit<false><<<blocks_for((P.n + 3u) / 4u), 256, 0, s>>>(P, D, hour_offset, zero_props ? 1u : 0u);
+    else k_commit_lanes<<<blocks_for((P.n + 32u * EPI_COMMIT_APT - 1u) / (32u * EPI_COMMIT_APT) * 32u), 256, 0, s>>>(P, D, hour_offset, zero_props ? 1u : 0u);
 }
 void launch_sleep(const Params& P, const DevPtrs& D, uint32_t hour_offset, cudaStream_t s) { k_sleep<<<blocks_for((P.n + 3u) / 4u), 256, 0, s>>>(P, D, hour_offset); }
 void launch_lock(const Params& P, const DevPtrs& D, cudaStream_t s) { k_lock<<<blocks_for(P.n), 256, 0, s>>>(P, D.st); }
