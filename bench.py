@@ -386,13 +386,13 @@ def run_ours(args):
         wl = WORKLOAD_NAMES[args.workload]
         if multi:
             wl = (f"BASELINE config #4/#5 pattern: {world} regions x {n} agents (each region = {wl}), travel plan with every ordered pair "
-                  f"{n // 1000} migrators/day (hours 48..336) and {n // 2000} commuters/day, one region per GPU, NCCL all-to-allv traveller exchange")
+                  f"{n // 1000} migrators/day (hours 48..336) and {n // 2000} commuters/day, one region per GPU, traveller exchange over NVLink peer memory / NCCL")
         line = {
             "metric": "agent-steps/sec", "value": value, "unit": "agent-steps/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": wl, "agents_per_gpu": n, "grid_size": kw["grid_size"], "step": "one simulated day (24 hours)",
                        "l2": "state + grids larger than L2 (no flush needed)" if n >= 5_000_000 else "working set fits the 126 MB L2; no flush (the real run is L2-resident too)",
-                       "regions": world, "exchange": "epi_exchange: pack -> grouped ncclSend/ncclRecv of the plan-bounded segments (count in the segment header) -> unpack, at h%24 in {0, 7, 17}" if multi else "n/a",
+                       "regions": world, "exchange": "epi_exchange at h%24 in {0, 7, 17}: one cooperative kernel (leave -> records pushed into the peers' memory over NVLink, CUDA IPC -> wait -> arrive); grouped ncclSend/ncclRecv when peers cannot be mapped" if multi else "n/a",
                        "phase": phase, "last_counts_row": last_row},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         }

@@ -32,7 +32,7 @@ if '--json' in sys.argv:
     j = {'k_hour': {'dram_bytes_per_launch': sum(map(byt, kh)) * unit / len(kh), 'launches_captured': len(kh)},
          'k_commit': {'dram_bytes_per_launch': sum(map(byt, kc)) * unit / len(kc), 'launches_captured': len(kc)},
          'workload': '10m',
-         'source': 'ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none on bench.py --steps 2 --warmup 3: every k_hour / k_commit launch of one simulated day (day 3), B200; profiles/r02b_launches_10m.csv'}
+         'source': 'ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none on bench.py --steps 2 --warmup 3: every k_hour / k_commit launch of one simulated day (day 3), B200; profiles/r02d_launches_10m.csv'}
     j['pass_dram_bytes_per_launch'] = j['k_hour']['dram_bytes_per_launch'] + j['k_commit']['dram_bytes_per_launch']
     # the 16 movement hours (h = 7..22) alone: the first 16 of the day's 18 k_hour / k_commit pairs (h = 23 and h = 0 follow)
     j['movement_pass_dram_bytes_per_launch'] = (sum(map(byt, kh[:16])) + sum(map(byt, kc[:16]))) / 16.0
