@@ -169,8 +169,8 @@ int epi_intervention_events(const epi_engine* e, epi_intervention_event* out, ui
 
 /* ---- multi-region: the traveller exchange (engine/src/epidemiology_simulation.rs:391-503) -------------------------------
  * Per exchange hour (h % 24 == 0 migrators inside the migration window, h % 24 in {7, 17} commuters) the caller runs
- *   epi_step(hour) -> epi_travel_pack -> all-to-all of the segments (NCCL over NVLink; torch.distributed in this repo)
- *   -> epi_travel_unpack -> epi_finish_hour.
+ *   epi_step(hour) -> epi_travel_pack -> all-to-all of the segments (the caller's transport; epi_exchange below is this
+ *   library's own, and the one the hour loop uses) -> epi_travel_unpack -> epi_finish_hour.
  * Replaces Transport::send_* / receive_* (engine/src/transport/mod.rs:34-42, mpi_transport.rs:78-215) around
  * remove_* / assimilate_* (allocation_map.rs:165-277).  Records never leave device memory and all of the reference's
  * sequential bookkeeping (allotment of migrators to regions, free agent slots, house / office occupancy heaps) runs on the
@@ -201,10 +201,14 @@ int epi_get_regions(epi_engine* e, uint32_t* reg);
 /* ---- multi-region: the Transport and the hour loop behind the ABI ---------------------------------------------------------
  * Replaces the reference's `Transport` trait (engine/src/transport/mod.rs:34-42) and its MPI implementation
  * (MpiTransport::send_commuters / send_migrators / receive_commuters / receive_migrators, transport/mpi_transport.rs:78-215:
- * bincode + snappy over MPI point-to-point) by an all-to-allv of packed 32-byte records between the GPUs: NCCL grouped
- * ncclSend / ncclRecv over NVLink / NVSwitch, one rank per region, everything queued on the engine's stream (pack kernels ->
- * collective -> unpack kernels, no host wait in between).  Each (source, destination) pair ships only the records the travel
- * plan can produce for it (the commute matrix entry; the migration matrix entry + 8 sigma), not a padded segment.
+ * bincode + snappy over MPI point-to-point) by an all-to-allv of packed 32-byte records between the GPUs, one rank per region,
+ * everything on the engine's stream with no host wait inside.  Two data planes, chosen at epi_comm_init by all ranks together:
+ *   peer memory (default): every rank maps the others' receive areas and flag words (CUDA IPC); an exchange is ONE cooperative
+ *     kernel that removes the leavers, stores each destination's records straight into that rank's receive area over NVLink /
+ *     NVSwitch, raises its flag there, waits for the peers' flags and installs the arrivals (csrc/travel.cu, k_travel_exchange);
+ *   NCCL (when a peer cannot be mapped, or EPI_NO_PEER=1): leave kernel -> grouped ncclSend / ncclRecv -> arrive kernel.
+ * Each (source, destination) pair ships only the records it has (peer memory) or the records the travel plan can produce for it
+ * (NCCL: the commute matrix entry; the migration matrix entry + 8 sigma), not a padded segment.
  *
  * epi_comm_unique_id: ncclGetUniqueId.  One rank calls it and hands the EPI_COMM_ID_BYTES bytes to the others by any means
  *   (a file, an environment variable, MPI_Bcast: the reference's ranks meet through mpirun, engine-app/src/main.rs:131-147).
@@ -221,8 +225,9 @@ int epi_comm_destroy(epi_engine* e);
 /* EPI_TRAVEL_MIGRATE / EPI_TRAVEL_COMMUTE when `hour` is an exchange hour of this engine's travel plan, -1 otherwise
  * (MpiTransport::receive_tick, mpi_transport.rs:60-76; migrators only inside the migration window, citizen/mod.rs:460-462) */
 int epi_exchange_kind(const epi_engine* e, uint32_t hour);
-/* One traveller exchange on an engine with an NCCL communicator: epi_travel_pack -> all-to-allv -> epi_travel_unpack, all
- * deferred (epi_finish_hour settles).  Every rank of the communicator must call it for the same (hour, kind).  The body of
+/* One traveller exchange on an engine with a communicator from epi_comm_init: leave -> records to the peers -> arrive (one
+ * cooperative kernel over peer memory, or pack -> ncclSend / ncclRecv -> unpack), all deferred: counts, population and errors
+ * stay on the device and surface at the next epi_collect_hours / epi_finish_hour.  Every rank of the communicator must call it for the same (hour, kind).  The body of
  * epidemiology_simulation.rs:407-488. */
 int epi_exchange(epi_engine* e, uint32_t hour, int kind);
 /* Epidemiology::run_multi_engine's hour loop (epidemiology_simulation.rs:331-537) for hours first_hour .. first_hour +
