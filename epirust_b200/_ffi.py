@@ -75,7 +75,7 @@ EXPORTS = [
     "epi_sync", "epi_reset", "epi_step", "epi_enqueue_hour", "epi_enqueue_hours", "epi_collect_hours", "epi_next_decision_hour", "epi_step_with_draws", "epi_run_hours", "epi_simulate_hours", "epi_intervention_events", "epi_lock_city", "epi_unlock_city", "epi_vaccinate",
     "epi_expand_hospital", "epi_get_state", "epi_set_state", "epi_build_population", "epi_population_size", "epi_geometry", "epi_get_grid", "epi_set_kernel_timing",
     "epi_get_kernel_times", "epi_get_hour_times", "epi_launch_count", "epi_device_bytes", "epi_epoch_resets", "epi_set_tiles", "epi_tile_hours", "epi_debug_trace", "epi_config_from_json", "epi_config_from_json_string",
-    "epi_run_standalone", "epi_version", "epi_device_count",
+    "epi_run_standalone", "epi_run_standalone_ex", "epi_config_citizen_state_messages", "epi_citizen_states", "epi_version", "epi_device_count",
     "epi_comm_unique_id", "epi_comm_init", "epi_comm_init_local", "epi_comm_destroy", "epi_exchange_kind", "epi_exchange", "epi_run_multi_hours",
     "epi_count_outgoing", "epi_outgoing_travels", "epi_should_terminate", "epi_multi_schedule_trace",
     "epi_configuration_read", "epi_configuration_free", "epi_configuration_regions", "epi_configuration_region_name", "epi_configuration_engine_config",
@@ -171,6 +171,9 @@ def load():
     L.epi_config_from_json.argtypes = [C.c_char_p, C.POINTER(EpiConfig)]
     L.epi_config_from_json_string.argtypes = [C.c_char_p, C.POINTER(EpiConfig)]
     L.epi_run_standalone.argtypes = [C.POINTER(EpiConfig), u64, i32, C.c_char_p, C.c_char_p, vp, u32, C.POINTER(u32), C.POINTER(C.c_double)]
+    L.epi_run_standalone_ex.argtypes = [C.POINTER(EpiConfig), u64, i32, C.c_char_p, C.c_char_p, i32, vp, u32, C.POINTER(u32), C.POINTER(C.c_double)]
+    L.epi_config_citizen_state_messages.argtypes = [C.c_char_p, C.POINTER(i32)]
+    L.epi_citizen_states.argtypes = [vp, vp, vp, vp, vp, u32, C.POINTER(u32)]
     L.epi_version.restype = C.c_char_p
     L.epi_comm_unique_id.argtypes = [vp]
     L.epi_comm_init.argtypes = [vp, i32, i32, vp]

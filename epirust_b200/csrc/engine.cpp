@@ -1042,6 +1042,31 @@ int epi_get_state(epi_engine* e, int32_t* cx, int32_t* cy, uint32_t* st, uint32_
     return EPI_OK;
 }
 
+int epi_citizen_states(epi_engine* e, char* state_out, int32_t* x_out, int32_t* y_out, uint32_t* slot_out, uint32_t capacity, uint32_t* n_out) {
+    if (!e || !n_out || (capacity && (!state_out || !x_out || !y_out))) return engine_fail(e, EPI_ERR_ARG, "null argument");
+    CU(cudaSetDevice(e->device));
+    const size_t n = e->P.n, nb = n * sizeof(uint32_t);
+    std::vector<uint32_t> cell(n), st(n);
+    CU(cudaMemcpyAsync(cell.data(), e->D.cell, nb, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaMemcpyAsync(st.data(), e->D.st, nb, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    static const char letters[5] = {'s', 'e', 'i', 'r', 'd'};  // CitizenState::state_str (citizen_state.rs:34-42)
+    uint32_t live = 0;
+    for (size_t i = 0; i < n; ++i) {
+        const uint32_t state = st[i] & ST_STATE_MASK;
+        if (state > ST_D) continue;  // empty slot
+        if (live < capacity) {
+            state_out[live] = letters[state];
+            x_out[live] = (int32_t)(cell[i] & CELL_XMASK);
+            y_out[live] = (int32_t)(cell[i] >> CELL_BITS);
+            if (slot_out) slot_out[live] = (uint32_t)i;
+        }
+        ++live;
+    }
+    *n_out = live;
+    return EPI_OK;
+}
+
 int epi_build_population(const epi_config* cfg, uint64_t seed, int32_t* cx, int32_t* cy, uint32_t* st, uint32_t* t0, uint32_t* home, uint32_t* work,
                          uint32_t* wsa) {
     if (!cfg || !cx || !cy || !st || !t0 || !home || !work || !wsa) return engine_fail(nullptr, EPI_ERR_ARG, "null argument");

@@ -101,7 +101,12 @@ int run_standalone(const Args& a) {
     uint32_t n_rows = 0;
     double secs = 0.0;
     // EngineApp::start_standalone always names the engine "0" (engine_app.rs:30,101)
-    const int rc = epi_run_standalone(&cfg, a.seed, a.device, a.output_dir.c_str(), "0", nullptr, 0, &n_rows, &secs);
+    int citizen_states = 0;  // Config.enable_citizen_state_messages (common/src/config/mod.rs:54-55)
+    if (epi_config_citizen_state_messages(config_file.c_str(), &citizen_states) != EPI_OK) {
+        std::fprintf(stderr, "engine-app: %s\n", epi_last_error(nullptr));
+        return 1;
+    }
+    const int rc = epi_run_standalone_ex(&cfg, a.seed, a.device, a.output_dir.c_str(), "0", citizen_states, nullptr, 0, &n_rows, &secs);
     if (rc != EPI_OK) {
         std::fprintf(stderr, "engine-app: error %d: %s\n", rc, epi_last_error(nullptr));
         return 1;

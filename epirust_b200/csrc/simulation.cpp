@@ -8,6 +8,7 @@
 #include <cstring>
 #include <ctime>
 #include <fstream>
+#include <sstream>
 
 #include "engine.h"
 #include "json.h"
@@ -130,7 +131,23 @@ static int simulate_hours(epi_engine* e, uint32_t first_hour, uint32_t n_hours, 
     return EPI_OK;
 }
 
-int run_single_engine(epi_engine* e, const epi_config& cfg, RunResult& result, bool log) {
+// EventsKafkaProducer::publish_citizen_states_buffer (events_kafka_producer.rs:62-67): serde_json of CitizenStatesAtHr, one line
+static int append_citizen_states(epi_engine* e, uint32_t hour, std::FILE* f) {
+    const uint32_t cap = epi_capacity(e);
+    std::vector<char> state(cap);
+    std::vector<int32_t> x(cap), y(cap);
+    std::vector<uint32_t> slot(cap);
+    uint32_t n = 0;
+    const int rc = epi_citizen_states(e, state.data(), x.data(), y.data(), slot.data(), cap, &n);
+    if (rc) return rc;
+    std::fprintf(f, "{\"hr\":%u,\"citizen_states\":[", hour);
+    for (uint32_t k = 0; k < n; ++k)
+        std::fprintf(f, "%s{\"citizen_id\":\"00000000-0000-4000-8000-%012x\",\"state\":\"%c\",\"location\":{\"x\":%d,\"y\":%d}}", k ? "," : "", slot[k], state[k], x[k], y[k]);
+    std::fprintf(f, "]}\n");
+    return std::ferror(f) ? engine_fail(e, EPI_ERR_IO, "cannot write the citizen states file") : EPI_OK;
+}
+
+int run_single_engine(epi_engine* e, const epi_config& cfg, RunResult& result, bool log, std::FILE* citizen_states) {
     epi_counts counts_at_hr;
     int rc = epi_counts_at_start(e, &counts_at_hr);
     if (rc) return rc;
@@ -139,8 +156,17 @@ int run_single_engine(epi_engine* e, const epi_config& cfg, RunResult& result, b
     result.rows.assign(cfg.hours > 0 ? cfg.hours : 1u, epi_counts{});
     uint32_t n_rows = 0;
     int stopped = 0;
-    if (cfg.hours > 1) {  // for simulation_hour in 1..config.get_hours()
+    if (cfg.hours > 1 && !citizen_states) {  // for simulation_hour in 1..config.get_hours()
         rc = simulate_hours(e, 1, cfg.hours - 1u, true, result.rows.data(), &n_rows, &stopped, log, &start_time);
+        if (rc) return rc;
+    }
+    // publish_citizen_state (allocation_map.rs:122-124): every agent's state after every hour -> the hours are run one at a time
+    for (uint32_t hour = 1; citizen_states && hour < cfg.hours && !stopped; ++hour) {
+        uint32_t got = 0;
+        rc = simulate_hours(e, hour, 1, true, result.rows.data() + n_rows, &got, &stopped, log, &start_time);
+        if (rc) return rc;
+        n_rows += got;
+        rc = append_citizen_states(e, hour, citizen_states);
         if (rc) return rc;
     }
     result.rows.resize(n_rows);
@@ -280,13 +306,56 @@ int epi_intervention_events(const epi_engine* e, epi_intervention_event* out, ui
 
 int epi_run_standalone(const epi_config* cfg, uint64_t seed, int device, const char* output_dir, const char* engine_id, epi_counts* rows_out,
                        uint32_t max_rows, uint32_t* n_rows, double* loop_seconds) {
+    return epi_run_standalone_ex(cfg, seed, device, output_dir, engine_id, 0, rows_out, max_rows, n_rows, loop_seconds);
+}
+
+int epi_config_citizen_state_messages(const char* json_path, int* on) {
+    if (!json_path || !on) return engine_fail(nullptr, EPI_ERR_ARG, "null argument");
+    *on = 0;
+    try {
+        std::ifstream in(json_path);
+        if (!in) return engine_fail(nullptr, EPI_ERR_IO, std::string("cannot open ") + json_path);
+        std::stringstream ss;
+        ss << in.rdbuf();
+        const JsonValue root = json_parse(ss.str());
+        if (const JsonValue* v = root.find("enable_citizen_state_messages")) *on = v->kind == JsonValue::Bool && v->b ? 1 : 0;
+    } catch (const std::exception& ex) {
+        return engine_fail(nullptr, EPI_ERR_CONFIG, ex.what());
+    }
+    return EPI_OK;
+}
+
+int epi_run_standalone_ex(const epi_config* cfg, uint64_t seed, int device, const char* output_dir, const char* engine_id, int citizen_state_messages,
+                          epi_counts* rows_out, uint32_t max_rows, uint32_t* n_rows, double* loop_seconds) {
     if (!cfg) return engine_fail(nullptr, EPI_ERR_ARG, "null config");
     epi_engine* e = nullptr;
     int rc = epi_create(cfg, seed, device, &e);
     if (rc) return rc;
     RunResult res;
     const bool log = std::getenv("EPI_LOG") != nullptr;
-    rc = run_single_engine(e, *cfg, res, log);
+    // the listeners take their file name when they are created (epidemiology_simulation.rs:141-150), i.e. before the hour loop
+    std::string base;
+    std::FILE* states = nullptr;
+    if (output_dir) {
+        try {
+            base = output_file_format(output_dir, engine_id ? engine_id : "0");
+        } catch (const std::exception& ex) {
+            epi_destroy(e);
+            return engine_fail(nullptr, EPI_ERR_IO, ex.what());
+        }
+        if (citizen_state_messages) {
+            states = std::fopen((base + "_citizen_states.jsonl").c_str(), "w");
+            if (!states) {
+                epi_destroy(e);
+                return engine_fail(nullptr, EPI_ERR_IO, "cannot create " + base + "_citizen_states.jsonl");
+            }
+        }
+    }
+    rc = run_single_engine(e, *cfg, res, log, states);
+    if (states) {
+        if (!rc) std::fputs("{\"simulation_ended\": true}\n", states);  // events_kafka_producer.rs:77-88
+        std::fclose(states);
+    }
     if (rc) {
         set_global_error(e->err);
         epi_destroy(e);
@@ -298,7 +367,7 @@ int epi_run_standalone(const epi_config* cfg, uint64_t seed, int device, const c
             Listeners l;
             l.counts = res.rows;
             l.interventions = res.interventions;
-            l.simulation_ended(output_file_format(output_dir, engine_id ? engine_id : "0"));
+            l.simulation_ended(base);
         } catch (const std::exception& ex) {
             return engine_fail(nullptr, EPI_ERR_IO, ex.what());
         }

@@ -1,6 +1,7 @@
 // Host side of the hour loop: the mirror of the reference's interventions, listeners and Epidemiology::run_single_engine,
 // driving the HBM-resident engine through the C ABI.
 #pragma once
+#include <cstdio>
 #include <map>
 #include <string>
 #include <vector>
@@ -111,6 +112,8 @@ void config_from_value(const JsonValue& root, epi_config& c);
 int process_interventions(epi_engine* e, const epi_counts& c, bool log);
 
 // Epidemiology::run_single_engine on an existing engine (epidemiology_simulation.rs:211-274).  Returns EPI_* code.
-int run_single_engine(epi_engine* e, const epi_config& cfg, RunResult& result, bool log);
+// citizen_states: when not null, the run goes hour by hour and appends one CitizenStatesAtHr JSON line per hour to it
+// (Config.enable_citizen_state_messages; listeners/events_kafka_producer.rs:62-100).
+int run_single_engine(epi_engine* e, const epi_config& cfg, RunResult& result, bool log, std::FILE* citizen_states = nullptr);
 
 }  // namespace epi

@@ -252,6 +252,15 @@ class Engine:
         self._check(self.L.epi_get_state(self.h, *[_ptr(arrs[f]) for f in STATE_FIELDS]))
         return arrs
 
+    def citizen_states(self):
+        """Listener::citizen_state_updated: (state letters as bytes 's','e','i','r','d', x, y, slot) of every live agent."""
+        n = self.capacity
+        state, x, y, slot = np.zeros(n, np.uint8), np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, np.uint32)
+        live = C.c_uint32()
+        self._check(self.L.epi_citizen_states(self.h, _ptr(state), _ptr(x), _ptr(y), _ptr(slot), n, C.byref(live)))
+        k = live.value
+        return state[:k], x[:k], y[:k], slot[:k]
+
     def set_state(self, arrs):
         a = [np.ascontiguousarray(arrs[f], dt) for f, dt in zip(STATE_FIELDS, STATE_DTYPES)]
         self._check(self.L.epi_set_state(self.h, len(a[0]), *[_ptr(x) for x in a]))

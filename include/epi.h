@@ -284,6 +284,12 @@ int epi_set_state(epi_engine* e, uint32_t n, const int32_t* cell_x, const int32_
 int epi_population_size(const epi_config* cfg, uint32_t* n);
 int epi_build_population(const epi_config* cfg, uint64_t seed, int32_t* cell_x, int32_t* cell_y, uint32_t* st, uint32_t* t0,
                          uint32_t* home, uint32_t* work, uint32_t* wsa);
+/* Listener::citizen_state_updated (engine/src/listeners/listener.rs:33; EventsKafkaProducer, listeners/events_kafka_producer.rs:90-100;
+ * CitizenState, models/events/citizen_state.rs:26-62): what the reference publishes per agent and hour on the
+ * `citizen_states_updated` topic when Config.enable_citizen_state_messages is set -- the state letter ('s', 'e', 'i', 'r', 'd':
+ * CitizenState::state_str) and the location of every live agent after the last simulated hour, in slot order; slot_out (may be
+ * NULL) receives the slot, this engine's stand-in for Citizen.id.  Up to `capacity` agents are written; *n_out = live agents. */
+int epi_citizen_states(epi_engine* e, char* state_out, int32_t* x_out, int32_t* y_out, uint32_t* slot_out, uint32_t capacity, uint32_t* n_out);
 /* out[0..3] housing sx,sy,ex,ey; [4..7] transport; [8..11] work; [12..15] hospital (current); [16] houses; [17] offices;
  * [18] grid_size.  (geography/mod.rs:33-70, grid.rs:240-261) */
 int epi_geometry(const epi_engine* e, int32_t* out19);
@@ -332,6 +338,16 @@ int epi_config_from_json_string(const char* json_text, epi_config* out);
  * hour-loop wall time (what the reference logs as Iterations/sec, epidemiology_simulation.rs:270-272). */
 int epi_run_standalone(const epi_config* cfg, uint64_t seed, int device, const char* output_dir, const char* engine_id,
                        epi_counts* rows_out, uint32_t max_rows, uint32_t* n_rows, double* loop_seconds);
+/* The same with Config.enable_citizen_state_messages (common/src/config/mod.rs:54-55, default false): when
+ * citizen_state_messages != 0 the run proceeds hour by hour and appends to <output_dir>/output/simulation_<engine_id>_<UTC>
+ * _citizen_states.jsonl one line per simulated hour, the JSON the reference's EventsKafkaProducer sends to the
+ * `citizen_states_updated` topic (serde of CitizenStatesAtHr: {"hr":H,"citizen_states":[{"citizen_id":"..","state":"s",
+ * "location":{"x":X,"y":Y}}, ..]}; citizen_id is a UUID-shaped rendering of the agent slot, the reference's is a random Uuid),
+ * and {"simulation_ended": true} as the last line (events_kafka_producer.rs:77-88).  There is no broker here: the file is the topic. */
+int epi_run_standalone_ex(const epi_config* cfg, uint64_t seed, int device, const char* output_dir, const char* engine_id, int citizen_state_messages,
+                          epi_counts* rows_out, uint32_t max_rows, uint32_t* n_rows, double* loop_seconds);
+/* Host only: Config.enable_citizen_state_messages of a simulation-config JSON file (absent = 0, serde default) */
+int epi_config_citizen_state_messages(const char* json_path, int* on);
 
 /* ---- host driver: multi-region runs (engine-app -m mpi) ----------------------------------------------------------------- */
 /* common::config::Configuration (common/src/config/configuration.rs:28-57): {engine_configs: [{engine_id, config}],

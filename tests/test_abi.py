@@ -99,3 +99,21 @@ def test_invalid_configs_are_rejected_before_touching_the_device():
                     (dict(n_agents=100, exposed=200), "starting infections")):
         with pytest.raises(EpiError, match=msg):
             Engine(make_config(**kw))
+
+
+def test_enable_citizen_state_messages_flag(tmp_path):
+    """Config.enable_citizen_state_messages is `#[serde(default)]` bool (common/src/config/mod.rs:54-55): absent = false."""
+    import ctypes as C
+    L = _ffi.load()
+    base = json.load(open(os.path.join(GOLDEN, "default_config.json")))
+    on = C.c_int(-1)
+    for value, expect in ((None, 0), (False, 0), (True, 1)):
+        cfg = dict(base)
+        cfg.pop("enable_citizen_state_messages", None)
+        if value is not None:
+            cfg["enable_citizen_state_messages"] = value
+        p = tmp_path / "c.json"
+        p.write_text(json.dumps(cfg))
+        assert L.epi_config_citizen_state_messages(str(p).encode(), C.byref(on)) == 0
+        assert on.value == expect
+    assert L.epi_config_citizen_state_messages(str(tmp_path / "missing.json").encode(), C.byref(on)) != 0

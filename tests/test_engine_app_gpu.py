@@ -40,6 +40,61 @@ def test_standalone_cli_writes_the_reference_outputs(tmp_path):
     assert [(e["hour"], e["intervention"]) for e in ev] == [(int(h), INTERVENTION_NAMES[int(k)]) for h, k, s in events_o]
 
 
+def test_citizen_state_messages_stream(tmp_path):
+    """Config.enable_citizen_state_messages (common/src/config/mod.rs:54-55): one CitizenStatesAtHr JSON line per simulated hour
+    (listeners/events_kafka_producer.rs:62-100, models/events/citizen_state.rs:26-62), the stand-in for the
+    `citizen_states_updated` topic.  Every line must agree with the oracle's agents of that hour: state letter and location per slot."""
+    B.build()
+    cfg = json.load(open(os.path.join(GOLDEN, "default_config.json")))
+    cfg["population"]["Auto"]["number_of_agents"] = 600
+    cfg["geography_parameters"]["grid_size"] = 80
+    cfg["hours"] = 60
+    cfg["starting_infections"] = {"infected_mild_asymptomatic": 5, "infected_mild_symptomatic": 5, "infected_severe": 5, "exposed": 20}
+    cfg["enable_citizen_state_messages"] = True
+    path = tmp_path / "with_states.json"
+    path.write_text(json.dumps(cfg))
+    r = subprocess.run([B.APP, "-c", str(path), "-o", str(tmp_path), "--seed", "3"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    (csv_path,) = glob.glob(str(tmp_path / "output" / "simulation_0_*[0-9].csv"))
+    rows = read_rows(csv_path)
+    (st_path,) = glob.glob(str(tmp_path / "output" / "simulation_0_*_citizen_states.jsonl"))
+    lines = open(st_path).read().splitlines()
+    assert json.loads(lines[-1]) == {"simulation_ended": True}
+    assert len(lines) == len(rows) + 1
+    from epirust_b200.engine import config_from_json
+    gcfg = config_from_json(str(path))
+    ocfg = O.EpiConfig()
+    for name, _ in O.EpiConfig._fields_:
+        v = getattr(gcfg, name)
+        if hasattr(v, "__len__") and not isinstance(v, (bytes, str)):
+            for i in range(len(v)):
+                getattr(ocfg, name)[i] = v[i]
+        else:
+            setattr(ocfg, name, v)
+    orc = O.OracleEngine(ocfg, seed=3)
+    letters = "seird"
+    for k, line in enumerate(lines[:-1]):
+        msg = json.loads(line)
+        hour = k + 1
+        assert msg["hr"] == hour
+        orc.step(hour)
+        st = orc.get_state()
+        got = msg["citizen_states"]
+        assert len(got) == 600
+        for slot, c in enumerate(got):
+            assert c["citizen_id"] == "00000000-0000-4000-8000-%012x" % slot
+            assert c["state"] == letters[int(st["st"][slot]) & 7]
+            assert (c["location"]["x"], c["location"]["y"]) == (int(st["cell_x"][slot]), int(st["cell_y"][slot]))
+        counts = [sum(1 for c in got if c["state"] == ch) for ch in letters]
+        assert counts == [int(rows[k][1]), int(rows[k][2]), int(rows[k][3]) + int(rows[k][4]), int(rows[k][5]), int(rows[k][6])]
+    # the flag is off by default: no such file
+    cfg["enable_citizen_state_messages"] = False
+    path.write_text(json.dumps(cfg))
+    r2 = subprocess.run([B.APP, "-c", str(path), "-o", str(tmp_path / "plain"), "--seed", "3"], capture_output=True, text=True, timeout=600)
+    assert r2.returncode == 0, r2.stderr
+    assert not glob.glob(str(tmp_path / "plain" / "output" / "*_citizen_states.jsonl"))
+
+
 def oracle_of(c, seed, hours):
     ocfgs = []
     for r in range(c.n_regions):
