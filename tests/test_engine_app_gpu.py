@@ -115,15 +115,20 @@ def oracle_of(c, seed, hours):
     return np.stack([orc.step(h) for h in range(1, hours)], axis=1)  # [region, hour, 7]
 
 
-def test_two_region_cli_one_region_per_gpu(tmp_path):
-    """`engine-app -m mpi`: the binary forks one process per region, one region per GPU, NCCL all-to-allv between them --
-    with nothing but the binary on PATH (no Python, no torchrun) -- against the multi-region oracle."""
+@pytest.mark.parametrize("data_plane", ["peer_memory", "nccl"])
+def test_two_region_cli_one_region_per_gpu(tmp_path, data_plane):
+    """`engine-app -m mpi`: the binary forks one process per region, one region per GPU, the traveller exchange between them --
+    with nothing but the binary on PATH (no Python, no torchrun) -- against the multi-region oracle.  Both data planes: the fused
+    kernel over NVLink peer memory (default) and leave -> grouped ncclSend / ncclRecv -> arrive (EPI_NO_PEER=1, what a box whose
+    GPUs cannot map each other's memory falls back to)."""
     if device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
     B.build()
     cfg_path = os.path.join(GOLDEN, "two_regions_config.json")
-    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "PYTHONPATH")}
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "PYTHONPATH", "EPI_NO_PEER")}
     env["PATH"] = "/nonexistent"
+    if data_plane == "nccl":
+        env["EPI_NO_PEER"] = "1"
     r = subprocess.run([B.APP, "-m", "mpi", "-c", cfg_path, "-o", str(tmp_path), "--seed", "9"], capture_output=True, text=True, timeout=900, env=env, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert r.stdout.count("MPI\n") == 2
